@@ -1,0 +1,810 @@
+// b200blur.cu -- implementation of the C ABI declared in include/b200blur.h.
+//
+// The thin layer that replaces the OpenCL plumbing of heterogeneous_blur.c / split_image_blur.c
+// (clCreateContext / clCreateCommandQueue / clCreateBuffer / clEnqueue{Write,NDRange,Read} / clFinish /
+// clGetEventProfilingInfo) with the CUDA runtime, plus the two stream engines that replace
+// the batch loop of heterogeneous_blur.c:418-600.  CUDA runtime only: no PyTorch, no OpenCL, no CPU fallback.
+#include "b200blur.h"
+
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "blur_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? B200BLUR_ERR_NOMEM                         \
+                        : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ||             \
+                           e_ == cudaErrorInvalidDevice)                                               \
+                            ? B200BLUR_ERR_NO_DEVICE                                                   \
+                            : B200BLUR_ERR_CUDA;                                                       \
+            return fail(code_, "%d - %s failed: %s", (int)e_, #expr, cudaGetErrorString(e_));          \
+        }                                                                                              \
+    } while (0)
+
+struct EventSlot {
+    cudaEvent_t start = nullptr, end = nullptr;
+    bool in_use = false;
+};
+
+}  // namespace
+
+struct b200blur_ctx {
+    int device = -1;
+    int sm_count = 0;
+    std::vector<cudaStream_t> queues;
+    std::vector<EventSlot> events;
+    std::vector<int> free_events;
+    int kernel_variant = 0;
+    int64_t launches = 0;
+    // ring of device buffers owned by b200blur_run_host
+    struct Slot {
+        uint8_t *d_in = nullptr, *d_out = nullptr;
+        cudaEvent_t ev[6] = {};  // h2d start/end, kernel start/end, d2h start/end
+    };
+    std::vector<Slot> ring;
+    size_t ring_slot_bytes = 0;
+};
+
+namespace {
+
+int ctx_check(const b200blur_ctx *ctx)
+{
+    if (!ctx) return fail(B200BLUR_ERR_INVALID, "context is NULL");
+    return B200BLUR_OK;
+}
+
+int queue_check(const b200blur_ctx *ctx, int queue)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (queue < 0 || queue >= (int)ctx->queues.size())
+        return fail(B200BLUR_ERR_INVALID, "queue %d out of range [0,%d)", queue, (int)ctx->queues.size());
+    return B200BLUR_OK;
+}
+
+int event_begin(b200blur_ctx *ctx, int queue, b200blur_event *ev, int *slot_out)
+{
+    *slot_out = -1;
+    if (!ev) return B200BLUR_OK;
+    int idx;
+    if (!ctx->free_events.empty()) {
+        idx = ctx->free_events.back();
+        ctx->free_events.pop_back();
+    } else {
+        EventSlot s;
+        CU_TRY(cudaEventCreate(&s.start));
+        CU_TRY(cudaEventCreate(&s.end));
+        ctx->events.push_back(s);
+        idx = (int)ctx->events.size() - 1;
+    }
+    ctx->events[idx].in_use = true;
+    CU_TRY(cudaEventRecord(ctx->events[idx].start, ctx->queues[queue]));
+    *slot_out = idx;
+    *ev = idx;
+    return B200BLUR_OK;
+}
+
+int event_end(b200blur_ctx *ctx, int queue, int slot)
+{
+    if (slot < 0) return B200BLUR_OK;
+    CU_TRY(cudaEventRecord(ctx->events[slot].end, ctx->queues[queue]));
+    return B200BLUR_OK;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool launch_vectorised(const b200blur_launch *l)
+{
+    const long long pitch = (long long)l->width * l->channels;
+    if (l->channels < 1 || l->channels > 4) return false;
+    if (pitch % 16 != 0) return false;
+    if (!aligned16(l->in) || !aligned16(l->out)) return false;
+    if (l->n_images > 1 && (l->in_image_stride % 16 || l->out_image_stride % 16)) return false;
+    if (l->halo_top && (!aligned16(l->halo_top) || (l->n_images > 1 && l->halo_top_stride % 16))) return false;
+    if (l->halo_bottom && (!aligned16(l->halo_bottom) || (l->n_images > 1 && l->halo_bottom_stride % 16)))
+        return false;
+    return true;
+}
+
+int launch_validate(const b200blur_launch *l)
+{
+    if (!l) return fail(B200BLUR_ERR_INVALID, "launch is NULL");
+    if (l->width < 0 || l->rows < 0 || l->n_images < 0 || l->channels < 1)
+        return fail(B200BLUR_ERR_INVALID, "negative size or channels < 1 (width %d rows %d channels %d n_images %lld)",
+                    l->width, l->rows, l->channels, (long long)l->n_images);
+    if (l->reserved != 0) return fail(B200BLUR_ERR_INVALID, "launch.reserved must be 0");
+    if ((long long)l->width * l->channels > 0x7fffffffLL)
+        return fail(B200BLUR_ERR_INVALID, "row pitch width*channels exceeds 2^31-1 bytes");
+    const bool empty = l->width == 0 || l->rows == 0 || l->n_images == 0;
+    if (!empty && (!l->in || !l->out)) return fail(B200BLUR_ERR_INVALID, "in/out pointer is NULL");
+    if (!empty && l->in == l->out) return fail(B200BLUR_ERR_INVALID, "in-place blur (in == out) is not supported");
+    return B200BLUR_OK;
+}
+
+b200blur::BandParams to_params(const b200blur_launch *l)
+{
+    b200blur::BandParams p;
+    p.in = static_cast<const uint8_t *>(l->in);
+    p.out = static_cast<uint8_t *>(l->out);
+    p.halo_top = static_cast<const uint8_t *>(l->halo_top);
+    p.halo_bot = static_cast<const uint8_t *>(l->halo_bottom);
+    p.in_stride = l->in_image_stride;
+    p.out_stride = l->out_image_stride;
+    p.top_stride = l->halo_top_stride;
+    p.bot_stride = l->halo_bottom_stride;
+    p.pitch = l->width * l->channels;
+    p.rows = l->rows;
+    p.width = l->width;
+    p.channels = l->channels;
+    p.n_images = l->n_images;
+    return p;
+}
+
+template <int RS>
+void launch_strip(const b200blur::BandParams &p, cudaStream_t s, long long img0, long long n)
+{
+    const int cpr = p.pitch / 16;
+    const int n_strips = (p.rows + RS - 1) / RS;
+    const long long units = (long long)cpr * n_strips;
+    const int block = 256;
+    b200blur::BandParams q = p;
+    q.in += (size_t)img0 * p.in_stride;
+    q.out += (size_t)img0 * p.out_stride;
+    if (q.halo_top) q.halo_top += (size_t)img0 * p.top_stride;
+    if (q.halo_bot) q.halo_bot += (size_t)img0 * p.bot_stride;
+    q.n_images = n;
+    dim3 grid((unsigned)n, (unsigned)((units + block - 1) / block));
+    switch (p.channels) {
+        case 1: b200blur::blur_strip_kernel<1, RS><<<grid, block, 0, s>>>(q, cpr, n_strips); break;
+        case 2: b200blur::blur_strip_kernel<2, RS><<<grid, block, 0, s>>>(q, cpr, n_strips); break;
+        case 3: b200blur::blur_strip_kernel<3, RS><<<grid, block, 0, s>>>(q, cpr, n_strips); break;
+        default: b200blur::blur_strip_kernel<4, RS><<<grid, block, 0, s>>>(q, cpr, n_strips); break;
+    }
+}
+
+// Launches the device code for one b200blur_launch on stream s.  Returns the number of kernels launched.
+int do_launch(b200blur_ctx *ctx, cudaStream_t s, const b200blur_launch *l, int *n_kernels)
+{
+    *n_kernels = 0;
+    if (l->width == 0 || l->rows == 0 || l->n_images == 0) return B200BLUR_OK;  // nothing to do
+    b200blur::BandParams p = to_params(l);
+    if (launch_vectorised(l)) {
+        // strip height: tall strips amortise the two halo rows; short strips expose more threads for small batches
+        const long long cpr = p.pitch / 16;
+        const long long threads_rs16 = cpr * ((p.rows + 15) / 16) * p.n_images;
+        const bool small = threads_rs16 < (long long)ctx->sm_count * 1024;
+        const long long max_grid_y = 65535;
+        if ((cpr * ((p.rows + 3) / 4) + 255) / 256 > max_grid_y)
+            return fail(B200BLUR_ERR_INVALID, "image too large for one launch (%lld chunks x %d rows)", cpr, p.rows);
+        const long long chunk = 0x7fffffffLL;
+        for (long long i0 = 0; i0 < p.n_images; i0 += chunk) {
+            const long long n = (p.n_images - i0 < chunk) ? p.n_images - i0 : chunk;
+            if (small) launch_strip<4>(p, s, i0, n);
+            else launch_strip<16>(p, s, i0, n);
+            ++*n_kernels;
+        }
+    } else {
+        const long long total = (long long)p.rows * p.pitch * p.n_images;
+        long long blocks = (total + 255) / 256;
+        const long long cap = (long long)ctx->sm_count * 32;
+        if (blocks > cap) blocks = cap;
+        b200blur::blur_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
+        ++*n_kernels;
+    }
+    CU_TRY(cudaGetLastError());
+    ctx->launches += *n_kernels;
+    return B200BLUR_OK;
+}
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// ============================================================================================== C ABI
+extern "C" {
+
+const char *b200blur_last_error(void) { return g_last_error.c_str(); }
+const char *b200blur_version(void) { return "b200blur 0.1.0 sm_100a"; }
+
+int b200blur_device_count(int *count)
+{
+    if (!count) return fail(B200BLUR_ERR_INVALID, "count is NULL");
+    *count = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200BLUR_ERR_NO_DEVICE, "%d - no CUDA device: %s", (int)e, cudaGetErrorString(e));
+    }
+    *count = n;
+    if (n == 0) return fail(B200BLUR_ERR_NO_DEVICE, "no CUDA device");
+    return B200BLUR_OK;
+}
+
+int b200blur_device_name(int device, char *buf, size_t buf_len)
+{
+    if (!buf || buf_len == 0) return fail(B200BLUR_ERR_INVALID, "buffer is NULL/empty");
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    snprintf(buf, buf_len, "%s", prop.name);
+    return B200BLUR_OK;
+}
+
+int b200blur_device_props(int device, int *sm_count, int *cc, size_t *global_mem_bytes)
+{
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc) *cc = prop.major * 10 + prop.minor;
+    if (global_mem_bytes) *global_mem_bytes = prop.totalGlobalMem;
+    return B200BLUR_OK;
+}
+
+int b200blur_ctx_create(int device, int n_queues, b200blur_ctx **out)
+{
+    if (!out) return fail(B200BLUR_ERR_INVALID, "ctx out-pointer is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (int rc = b200blur_device_count(&n)) return rc;
+    if (device < 0 || device >= n) return fail(B200BLUR_ERR_NO_DEVICE, "device %d out of range [0,%d)", device, n);
+    if (n_queues <= 0) n_queues = 4;
+    if (n_queues > 64) return fail(B200BLUR_ERR_INVALID, "n_queues %d > 64", n_queues);
+    CU_TRY(cudaSetDevice(device));
+    b200blur_ctx *ctx = new (std::nothrow) b200blur_ctx;
+    if (!ctx) return fail(B200BLUR_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(B200BLUR_ERR_CUDA, "%d - cudaGetDeviceProperties: %s", (int)e, cudaGetErrorString(e));
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < n_queues; i++) {
+        cudaStream_t s;
+        e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            for (auto q : ctx->queues) cudaStreamDestroy(q);
+            delete ctx;
+            return fail(B200BLUR_ERR_CUDA, "%d - cudaStreamCreate: %s", (int)e, cudaGetErrorString(e));
+        }
+        ctx->queues.push_back(s);
+    }
+    *out = ctx;
+    return B200BLUR_OK;
+}
+
+static void ring_release(b200blur_ctx *ctx)
+{
+    for (auto &s : ctx->ring) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        for (auto &e : s.ev)
+            if (e) cudaEventDestroy(e);
+    }
+    ctx->ring.clear();
+    ctx->ring_slot_bytes = 0;
+}
+
+int b200blur_ctx_destroy(b200blur_ctx *ctx)
+{
+    if (!ctx) return B200BLUR_OK;
+    cudaSetDevice(ctx->device);
+    for (auto q : ctx->queues) cudaStreamSynchronize(q);
+    ring_release(ctx);
+    for (auto &e : ctx->events) {
+        if (e.start) cudaEventDestroy(e.start);
+        if (e.end) cudaEventDestroy(e.end);
+    }
+    for (auto q : ctx->queues) cudaStreamDestroy(q);
+    delete ctx;
+    return B200BLUR_OK;
+}
+
+int b200blur_ctx_device(const b200blur_ctx *ctx) { return ctx ? ctx->device : -1; }
+int b200blur_ctx_num_queues(const b200blur_ctx *ctx) { return ctx ? (int)ctx->queues.size() : 0; }
+void *b200blur_ctx_queue_handle(const b200blur_ctx *ctx, int queue)
+{
+    if (!ctx || queue < 0 || queue >= (int)ctx->queues.size()) return nullptr;
+    return (void *)ctx->queues[queue];
+}
+int64_t b200blur_ctx_launch_count(const b200blur_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b200blur_set_kernel_variant(b200blur_ctx *ctx, int variant)
+{
+    if (!ctx) return 0;
+    int prev = ctx->kernel_variant;
+    ctx->kernel_variant = variant;
+    return prev;
+}
+
+// ------------------------------------------------------------------------------------------------- memory
+int b200blur_dev_alloc(b200blur_ctx *ctx, size_t bytes, void **dptr)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (!dptr) return fail(B200BLUR_ERR_INVALID, "dptr is NULL");
+    *dptr = nullptr;
+    CU_TRY(cudaSetDevice(ctx->device));
+    if (bytes == 0) bytes = 16;
+    CU_TRY(cudaMalloc(dptr, bytes));
+    return B200BLUR_OK;
+}
+
+int b200blur_dev_free(b200blur_ctx *ctx, void *dptr)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (!dptr) return B200BLUR_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaFree(dptr));
+    return B200BLUR_OK;
+}
+
+int b200blur_host_alloc(size_t bytes, void **hptr)
+{
+    if (!hptr) return fail(B200BLUR_ERR_INVALID, "hptr is NULL");
+    *hptr = nullptr;
+    if (bytes == 0) bytes = 16;
+    CU_TRY(cudaHostAlloc(hptr, bytes, cudaHostAllocPortable));
+    return B200BLUR_OK;
+}
+
+int b200blur_host_free(void *hptr)
+{
+    if (!hptr) return B200BLUR_OK;
+    CU_TRY(cudaFreeHost(hptr));
+    return B200BLUR_OK;
+}
+
+int b200blur_host_register(void *hptr, size_t bytes)
+{
+    if (!hptr) return fail(B200BLUR_ERR_INVALID, "hptr is NULL");
+    CU_TRY(cudaHostRegister(hptr, bytes, cudaHostRegisterPortable));
+    return B200BLUR_OK;
+}
+
+int b200blur_host_unregister(void *hptr)
+{
+    if (!hptr) return B200BLUR_OK;
+    CU_TRY(cudaHostUnregister(hptr));
+    return B200BLUR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- events
+int b200blur_event_ms(b200blur_ctx *ctx, b200blur_event ev, double *ms)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (!ms) return fail(B200BLUR_ERR_INVALID, "ms is NULL");
+    if (ev < 0 || ev >= (int)ctx->events.size() || !ctx->events[ev].in_use)
+        return fail(B200BLUR_ERR_INVALID, "event %d is not live", (int)ev);
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaEventSynchronize(ctx->events[ev].end));
+    float f = 0.f;
+    CU_TRY(cudaEventElapsedTime(&f, ctx->events[ev].start, ctx->events[ev].end));
+    *ms = f;
+    return B200BLUR_OK;
+}
+
+int b200blur_event_release(b200blur_ctx *ctx, b200blur_event ev)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (ev < 0 || ev >= (int)ctx->events.size() || !ctx->events[ev].in_use)
+        return fail(B200BLUR_ERR_INVALID, "event %d is not live", (int)ev);
+    ctx->events[ev].in_use = false;
+    ctx->free_events.push_back(ev);
+    return B200BLUR_OK;
+}
+
+int b200blur_enqueue_marker(b200blur_ctx *ctx, int queue, b200blur_event *ev)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    if (!ev) return fail(B200BLUR_ERR_INVALID, "ev is NULL");
+    CU_TRY(cudaSetDevice(ctx->device));
+    int slot;
+    if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
+    return event_end(ctx, queue, slot);
+}
+
+int b200blur_events_elapsed_ms(b200blur_ctx *ctx, b200blur_event from, b200blur_event to, double *ms)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (!ms) return fail(B200BLUR_ERR_INVALID, "ms is NULL");
+    for (b200blur_event ev : {from, to})
+        if (ev < 0 || ev >= (int)ctx->events.size() || !ctx->events[ev].in_use)
+            return fail(B200BLUR_ERR_INVALID, "event %d is not live", (int)ev);
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaEventSynchronize(ctx->events[from].end));
+    CU_TRY(cudaEventSynchronize(ctx->events[to].end));
+    float f = 0.f;
+    CU_TRY(cudaEventElapsedTime(&f, ctx->events[from].end, ctx->events[to].end));
+    *ms = f;
+    return B200BLUR_OK;
+}
+
+int b200blur_enqueue_wait(b200blur_ctx *ctx, int queue, b200blur_event ev)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    if (ev < 0 || ev >= (int)ctx->events.size() || !ctx->events[ev].in_use)
+        return fail(B200BLUR_ERR_INVALID, "event %d is not live", (int)ev);
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaStreamWaitEvent(ctx->queues[queue], ctx->events[ev].end, 0));
+    return B200BLUR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- transfers
+int b200blur_enqueue_write(b200blur_ctx *ctx, int queue, void *dst_dev, const void *src_host, size_t bytes,
+                           b200blur_event *ev)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    if (bytes && (!dst_dev || !src_host)) return fail(B200BLUR_ERR_INVALID, "NULL pointer in enqueue_write");
+    CU_TRY(cudaSetDevice(ctx->device));
+    int slot;
+    if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
+    if (bytes) CU_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->queues[queue]));
+    return event_end(ctx, queue, slot);
+}
+
+int b200blur_enqueue_read(b200blur_ctx *ctx, int queue, void *dst_host, const void *src_dev, size_t bytes,
+                          b200blur_event *ev)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    if (bytes && (!dst_host || !src_dev)) return fail(B200BLUR_ERR_INVALID, "NULL pointer in enqueue_read");
+    CU_TRY(cudaSetDevice(ctx->device));
+    int slot;
+    if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
+    if (bytes) CU_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->queues[queue]));
+    return event_end(ctx, queue, slot);
+}
+
+int b200blur_enqueue_write_2d(b200blur_ctx *ctx, int queue, void *dst_dev, size_t dst_pitch, const void *src_host,
+                              size_t src_pitch, size_t row_bytes, size_t rows, b200blur_event *ev)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    if (row_bytes && rows && (!dst_dev || !src_host)) return fail(B200BLUR_ERR_INVALID, "NULL pointer in enqueue_write_2d");
+    CU_TRY(cudaSetDevice(ctx->device));
+    int slot;
+    if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
+    if (row_bytes && rows)
+        CU_TRY(cudaMemcpy2DAsync(dst_dev, dst_pitch, src_host, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice,
+                                 ctx->queues[queue]));
+    return event_end(ctx, queue, slot);
+}
+
+int b200blur_enqueue_read_2d(b200blur_ctx *ctx, int queue, void *dst_host, size_t dst_pitch, const void *src_dev,
+                             size_t src_pitch, size_t row_bytes, size_t rows, b200blur_event *ev)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    if (row_bytes && rows && (!dst_host || !src_dev)) return fail(B200BLUR_ERR_INVALID, "NULL pointer in enqueue_read_2d");
+    CU_TRY(cudaSetDevice(ctx->device));
+    int slot;
+    if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
+    if (row_bytes && rows)
+        CU_TRY(cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost,
+                                 ctx->queues[queue]));
+    return event_end(ctx, queue, slot);
+}
+
+int b200blur_finish(b200blur_ctx *ctx, int queue)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaStreamSynchronize(ctx->queues[queue]));
+    return B200BLUR_OK;
+}
+
+int b200blur_finish_all(b200blur_ctx *ctx)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    CU_TRY(cudaSetDevice(ctx->device));
+    for (auto q : ctx->queues) CU_TRY(cudaStreamSynchronize(q));
+    return B200BLUR_OK;
+}
+
+// -------------------------------------------------------------------------------------------- kernel launch
+int b200blur_launch_rows(b200blur_launch *l, const void *in, void *out, int width, int in_height, int channels,
+                         int first_row, int n_rows, int64_t n_images, size_t in_image_stride,
+                         size_t out_image_stride)
+{
+    if (!l) return fail(B200BLUR_ERR_INVALID, "launch is NULL");
+    if (width < 0 || in_height < 0 || channels < 1 || first_row < 0 || n_rows < 0 || n_images < 0 ||
+        (long long)first_row + n_rows > in_height)
+        return fail(B200BLUR_ERR_INVALID, "bad geometry: width %d in_height %d channels %d rows [%d,%d+%d)", width,
+                    in_height, channels, first_row, first_row, n_rows);
+    const size_t pitch = (size_t)width * channels;
+    const uint8_t *base = static_cast<const uint8_t *>(in);
+    memset(l, 0, sizeof *l);
+    l->in = base ? base + (size_t)first_row * pitch : nullptr;
+    l->out = out;
+    l->width = width;
+    l->channels = channels;
+    l->rows = n_rows;
+    l->n_images = n_images;
+    l->in_image_stride = in_image_stride;
+    l->out_image_stride = out_image_stride;
+    if (base && n_rows > 0 && first_row > 0) {
+        l->halo_top = base + (size_t)(first_row - 1) * pitch;
+        l->halo_top_stride = in_image_stride;
+    }
+    if (base && n_rows > 0 && first_row + n_rows < in_height) {
+        l->halo_bottom = base + (size_t)(first_row + n_rows) * pitch;
+        l->halo_bottom_stride = in_image_stride;
+    }
+    return B200BLUR_OK;
+}
+
+int b200blur_launch_is_vectorised(const b200blur_launch *launch)
+{
+    if (!launch) return 0;
+    return launch_vectorised(launch) ? 1 : 0;
+}
+
+int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200blur_launch *launch, b200blur_event *ev)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    if (int rc = launch_validate(launch)) return rc;
+    CU_TRY(cudaSetDevice(ctx->device));
+    int slot;
+    if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
+    int nk;
+    if (int rc = do_launch(ctx, ctx->queues[queue], launch, &nk)) return rc;
+    return event_end(ctx, queue, slot);
+}
+
+// ----------------------------------------------------------------------------------- work distribution (L4)
+int b200blur_partition(int64_t n_items, int n_parts, int part, int64_t *begin, int64_t *count)
+{
+    if (n_items < 0 || n_parts < 1 || part < 0 || part >= n_parts || !begin || !count)
+        return fail(B200BLUR_ERR_INVALID, "bad partition request (%lld items, part %d of %d)", (long long)n_items, part,
+                    n_parts);
+    const int64_t q = n_items / n_parts, r = n_items % n_parts;
+    *begin = part * q + (part < r ? part : r);
+    *count = q + (part < r ? 1 : 0);
+    return B200BLUR_OK;
+}
+
+int b200blur_ratio_split_images(int batch_count, float gpu_ratio, int mode, int *n_first, int *n_second)
+{
+    if (batch_count < 0 || !n_first || !n_second || mode < 0 || mode > 2)
+        return fail(B200BLUR_ERR_INVALID, "bad ratio split request");
+    int second = 0, first = 0;
+    if (mode == 0) {
+        second = (int)(batch_count * gpu_ratio);
+        first = batch_count - second;
+    } else if (mode == 1) {
+        first = batch_count;
+    } else {
+        second = batch_count;
+    }
+    *n_first = first;
+    *n_second = second;
+    return B200BLUR_OK;
+}
+
+int b200blur_ratio_split_row(int height, float gpu_ratio, int *split_row)
+{
+    if (height < 2 || !split_row) return fail(B200BLUR_ERR_INVALID, "bad split-row request (height %d)", height);
+    int s = (int)(height * (1.0f - gpu_ratio));
+    if (s < 1) s = 1;
+    if (s > height - 1) s = height - 1;
+    *split_row = s;
+    return B200BLUR_OK;
+}
+
+// ------------------------------------------------------------------------------------------- stream engines
+int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int width, int height, int channels,
+                          int64_t n_images, int batch_size, int coalesce, b200blur_stats *stats)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (batch_size < 1) return fail(B200BLUR_ERR_INVALID, "batch_size %d < 1", batch_size);
+    if (width < 0 || height < 0 || channels < 1 || n_images < 0) return fail(B200BLUR_ERR_INVALID, "bad geometry");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const size_t image_bytes = (size_t)width * height * channels;
+    cudaStream_t s = ctx->queues[0];
+    const double t0 = now_ms();
+    b200blur_event ev_all = -1;
+    int slot = -1;
+    if (stats)
+        if (int rc = event_begin(ctx, 0, &ev_all, &slot)) return rc;
+    int64_t launches = 0;
+    const int64_t step = coalesce ? (n_images > 0 ? n_images : 1) : batch_size;
+    for (int64_t i0 = 0; i0 < n_images; i0 += step) {
+        const int64_t n = (n_images - i0 < step) ? n_images - i0 : step;
+        b200blur_launch l;
+        if (int rc = b200blur_launch_rows(&l, static_cast<const uint8_t *>(d_in) + (size_t)i0 * image_bytes,
+                                          static_cast<uint8_t *>(d_out) + (size_t)i0 * image_bytes, width, height,
+                                          channels, 0, height, n, image_bytes, image_bytes))
+            return rc;
+        if (int rc = launch_validate(&l)) return rc;
+        int nk;
+        if (int rc = do_launch(ctx, s, &l, &nk)) return rc;
+        launches += nk;
+    }
+    if (stats) {
+        if (int rc = event_end(ctx, 0, slot)) return rc;
+        double ms = 0;
+        if (int rc = b200blur_event_ms(ctx, ev_all, &ms)) return rc;
+        b200blur_event_release(ctx, ev_all);
+        memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = ms;
+        stats->images = n_images;
+        stats->launches = launches;
+        stats->wall_ms = now_ms() - t0;
+    }
+    return B200BLUR_OK;
+}
+
+static int ring_prepare(b200blur_ctx *ctx, size_t slot_bytes, int n_slots)
+{
+    if (ctx->ring_slot_bytes >= slot_bytes && (int)ctx->ring.size() == n_slots) return B200BLUR_OK;
+    ring_release(ctx);
+    ctx->ring.resize(n_slots);
+    for (auto &s : ctx->ring) {
+        CU_TRY(cudaMalloc((void **)&s.d_in, slot_bytes ? slot_bytes : 16));
+        CU_TRY(cudaMalloc((void **)&s.d_out, slot_bytes ? slot_bytes : 16));
+        for (auto &e : s.ev) CU_TRY(cudaEventCreate(&e));
+    }
+    ctx->ring_slot_bytes = slot_bytes;
+    return B200BLUR_OK;
+}
+
+int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int width, int height, int channels,
+                      int64_t n_images, int batch_size, b200blur_stats *stats)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (batch_size < 1) return fail(B200BLUR_ERR_INVALID, "batch_size %d < 1", batch_size);
+    if (width < 0 || height < 0 || channels < 1 || n_images < 0) return fail(B200BLUR_ERR_INVALID, "bad geometry");
+    if (ctx->queues.size() < 3) return fail(B200BLUR_ERR_INVALID, "run_host needs a context with >= 3 queues");
+    const size_t image_bytes = (size_t)width * height * channels;
+    if (n_images && image_bytes && (!h_in || !h_out)) return fail(B200BLUR_ERR_INVALID, "host pointer is NULL");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int n_slots = 4;
+    if (int rc = ring_prepare(ctx, image_bytes * (size_t)batch_size, n_slots)) return rc;
+    cudaStream_t q_in = ctx->queues[0], q_k = ctx->queues[1], q_out = ctx->queues[2];
+    const double t0 = now_ms();
+    double ms_in = 0, ms_k = 0, ms_out = 0;
+    int64_t launches = 0;
+    const int64_t n_chunks = (n_images + batch_size - 1) / batch_size;
+
+    auto harvest = [&](b200blur_ctx::Slot &s) -> int {
+        CU_TRY(cudaEventSynchronize(s.ev[5]));
+        float f;
+        CU_TRY(cudaEventElapsedTime(&f, s.ev[0], s.ev[1])); ms_in += f;
+        CU_TRY(cudaEventElapsedTime(&f, s.ev[2], s.ev[3])); ms_k += f;
+        CU_TRY(cudaEventElapsedTime(&f, s.ev[4], s.ev[5])); ms_out += f;
+        return B200BLUR_OK;
+    };
+
+    for (int64_t ci = 0; ci < n_chunks; ci++) {
+        b200blur_ctx::Slot &s = ctx->ring[ci % n_slots];
+        if (ci >= n_slots)
+            if (int rc = harvest(s)) return rc;  // slot's previous chunk fully drained (also frees d_in/d_out)
+        const int64_t i0 = ci * batch_size;
+        const int64_t n = (n_images - i0 < batch_size) ? n_images - i0 : batch_size;
+        const size_t bytes = (size_t)n * image_bytes;
+        // H2D
+        CU_TRY(cudaEventRecord(s.ev[0], q_in));
+        if (bytes)
+            CU_TRY(cudaMemcpyAsync(s.d_in, static_cast<const uint8_t *>(h_in) + (size_t)i0 * image_bytes, bytes,
+                                   cudaMemcpyHostToDevice, q_in));
+        CU_TRY(cudaEventRecord(s.ev[1], q_in));
+        // blur
+        CU_TRY(cudaStreamWaitEvent(q_k, s.ev[1], 0));
+        CU_TRY(cudaEventRecord(s.ev[2], q_k));
+        b200blur_launch l;
+        if (int rc = b200blur_launch_rows(&l, s.d_in, s.d_out, width, height, channels, 0, height, n, image_bytes,
+                                          image_bytes))
+            return rc;
+        int nk;
+        if (int rc = do_launch(ctx, q_k, &l, &nk)) return rc;
+        launches += nk;
+        CU_TRY(cudaEventRecord(s.ev[3], q_k));
+        // D2H
+        CU_TRY(cudaStreamWaitEvent(q_out, s.ev[3], 0));
+        CU_TRY(cudaEventRecord(s.ev[4], q_out));
+        if (bytes)
+            CU_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(h_out) + (size_t)i0 * image_bytes, s.d_out, bytes,
+                                   cudaMemcpyDeviceToHost, q_out));
+        CU_TRY(cudaEventRecord(s.ev[5], q_out));
+    }
+    const int64_t first_pending = n_chunks > n_slots ? n_chunks - n_slots : 0;
+    for (int64_t ci = first_pending; ci < n_chunks; ci++)
+        if (int rc = harvest(ctx->ring[ci % n_slots])) return rc;
+    CU_TRY(cudaStreamSynchronize(q_out));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->wall_ms = now_ms() - t0;
+        stats->h2d_ms = ms_in;
+        stats->kernel_ms = ms_k;
+        stats->d2h_ms = ms_out;
+        stats->images = n_images;
+        stats->launches = launches;
+        stats->h2d_bytes = (int64_t)(image_bytes * (size_t)n_images);
+        stats->d2h_bytes = (int64_t)(image_bytes * (size_t)n_images);
+    }
+    return B200BLUR_OK;
+}
+
+// -------------------------------------------------------------------------------- multi-GPU (Approach 2 bands)
+int b200blur_peer_enable(b200blur_ctx *a, b200blur_ctx *b)
+{
+    if (!a || !b) return fail(B200BLUR_ERR_INVALID, "context is NULL");
+    if (a->device == b->device) return B200BLUR_OK;
+    int ab = 0, ba = 0;
+    CU_TRY(cudaDeviceCanAccessPeer(&ab, a->device, b->device));
+    CU_TRY(cudaDeviceCanAccessPeer(&ba, b->device, a->device));
+    if (!ab || !ba) return fail(B200BLUR_ERR_PEER, "no peer access between devices %d and %d", a->device, b->device);
+    CU_TRY(cudaSetDevice(a->device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(B200BLUR_ERR_PEER, "%d - cudaDeviceEnablePeerAccess: %s", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    CU_TRY(cudaSetDevice(b->device));
+    e = cudaDeviceEnablePeerAccess(a->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(B200BLUR_ERR_PEER, "%d - cudaDeviceEnablePeerAccess: %s", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    return B200BLUR_OK;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == B200BLUR_IPC_HANDLE_BYTES, "IPC handle size");
+
+int b200blur_ipc_export(b200blur_ctx *ctx, void *dptr, unsigned char handle[B200BLUR_IPC_HANDLE_BYTES])
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (!dptr || !handle) return fail(B200BLUR_ERR_INVALID, "NULL pointer in ipc_export");
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, sizeof h);
+    return B200BLUR_OK;
+}
+
+int b200blur_ipc_open(b200blur_ctx *ctx, const unsigned char handle[B200BLUR_IPC_HANDLE_BYTES], void **dptr)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (!dptr || !handle) return fail(B200BLUR_ERR_INVALID, "NULL pointer in ipc_open");
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CU_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200BLUR_OK;
+}
+
+int b200blur_ipc_close(b200blur_ctx *ctx, void *dptr)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (!dptr) return B200BLUR_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaIpcCloseMemHandle(dptr));
+    return B200BLUR_OK;
+}
+
+}  // extern "C"

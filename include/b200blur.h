@@ -1,0 +1,217 @@
+/*
+ * b200blur.h -- C ABI of the B200-native 3x3 Gaussian-blur stream engine.
+ *
+ * This header is the drop-in boundary for the one hot path of CC834/Heterogeneous-OpenCL-Image-Processing-Engine:
+ * it replaces, call for call, the OpenCL host API that heterogeneous_blur.c and split_image_blur.c use inline
+ * from main().  Plain C: opaque handles, raw pointers and sizes, int status returns.
+ * No PyTorch, no OpenCL, no CPU fallback -- every compute entry point runs hand-written sm_100a CUDA and fails
+ * with B200BLUR_ERR_NO_DEVICE when no CUDA device is present.
+ *
+ * Reference citations are `file:line` relative to the reference repository root
+ * (A1 = heterogeneous_blur.c, A2 = split_image_blur.c, K = gaussian_kernel.cl).
+ *
+ * Threading: one host thread per GPU may call into distinct contexts concurrently (the reference is single
+ * threaded with two asynchronous queues, A1:201-212).  A context must not be used by two threads at once.
+ * b200blur_last_error() is thread-local.
+ */
+#ifndef B200BLUR_H
+#define B200BLUR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B200BLUR_API
+#else
+#define B200BLUR_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------------------------------ status */
+enum {
+    B200BLUR_OK = 0,
+    B200BLUR_ERR_INVALID = -1,   /* bad argument (NULL, negative size, misuse)                                */
+    B200BLUR_ERR_NO_DEVICE = -2, /* no CUDA device / device index out of range (A1:181-184 "Could not find")  */
+    B200BLUR_ERR_CUDA = -3,      /* a CUDA runtime call failed; b200blur_last_error() carries its message      */
+    B200BLUR_ERR_NOMEM = -4,     /* allocation failed (A1:434-437)                                            */
+    B200BLUR_ERR_PEER = -5       /* peer access between the two devices is not available                      */
+};
+
+/* Message of the last failure on the calling thread ("" if none).  Replaces cl_error()'s code+string (A1:25-30). */
+B200BLUR_API const char *b200blur_last_error(void);
+/* "b200blur <semver> sm_100a" */
+B200BLUR_API const char *b200blur_version(void);
+
+/* ---------------------------------------------------------------------------------------- device discovery
+ * Replaces clGetPlatformIDs / clGetDeviceIDs / clGetDeviceInfo (A1:144-191, A2:179-226). */
+B200BLUR_API int b200blur_device_count(int *count);
+B200BLUR_API int b200blur_device_name(int device, char *buf, size_t buf_len);
+/* sm count, compute capability major*10+minor, total global memory bytes; any pointer may be NULL. */
+B200BLUR_API int b200blur_device_props(int device, int *sm_count, int *cc, size_t *global_mem_bytes);
+
+/* ------------------------------------------------------------------------------------------------ context
+ * One per GPU.  Replaces clCreateContext + clCreateCommandQueueWithProperties(PROFILING_ENABLE) +
+ * clCreateProgramWithSource/clBuildProgram/clCreateKernel (A1:194-322, A2:229-353): the kernel is compiled ahead
+ * of time into this library, so there is no .cl file to find at run time (A1:222-226).
+ * `n_queues` in-order queues (CUDA streams) are created; queue 0..n_queues-1 are addressed by index.
+ * Pass n_queues <= 0 for the default (4). */
+typedef struct b200blur_ctx b200blur_ctx;
+B200BLUR_API int b200blur_ctx_create(int device, int n_queues, b200blur_ctx **ctx);
+B200BLUR_API int b200blur_ctx_destroy(b200blur_ctx *ctx); /* clRelease* (A1:727-744) */
+B200BLUR_API int b200blur_ctx_device(const b200blur_ctx *ctx);
+B200BLUR_API int b200blur_ctx_num_queues(const b200blur_ctx *ctx);
+/* The CUstream/cudaStream_t behind a queue, as an opaque pointer (for callers that bring their own events). */
+B200BLUR_API void *b200blur_ctx_queue_handle(const b200blur_ctx *ctx, int queue);
+
+/* ------------------------------------------------------------------------------------------------- memory
+ * dev_alloc/dev_free replace clCreateBuffer/clReleaseMemObject (A1:341-353, :727-730).
+ * host_alloc/host_free replace the per-batch malloc/free of the staging buffers (A1:431-432, :596-597) with
+ * page-locked memory so H2D/D2H run asynchronously at link speed; host_register pins a buffer the caller
+ * already owns. */
+B200BLUR_API int b200blur_dev_alloc(b200blur_ctx *ctx, size_t bytes, void **dptr);
+B200BLUR_API int b200blur_dev_free(b200blur_ctx *ctx, void *dptr);
+B200BLUR_API int b200blur_host_alloc(size_t bytes, void **hptr);
+B200BLUR_API int b200blur_host_free(void *hptr);
+B200BLUR_API int b200blur_host_register(void *hptr, size_t bytes);
+B200BLUR_API int b200blur_host_unregister(void *hptr);
+
+/* ------------------------------------------------------------------------------------------------- events
+ * Every enqueue can return an event handle that records the command's start and end on the device, like the
+ * cl_event of a PROFILING_ENABLE queue (A1:502-533).  event_ms = (END - START) in ms, the quantity summed at
+ * A1:544-579.  Handles are small integers owned by the context; release returns them to its pool. */
+typedef int32_t b200blur_event;
+#define B200BLUR_NO_EVENT ((b200blur_event *)0)
+B200BLUR_API int b200blur_event_ms(b200blur_ctx *ctx, b200blur_event ev, double *ms); /* clGetEventProfilingInfo */
+B200BLUR_API int b200blur_event_release(b200blur_ctx *ctx, b200blur_event ev);        /* clReleaseEvent          */
+/* clEnqueueMarker: an event that completes when everything enqueued on `queue` so far has completed. */
+B200BLUR_API int b200blur_enqueue_marker(b200blur_ctx *ctx, int queue, b200blur_event *ev);
+/* Device time in ms from the END of `from` to the END of `to` (both must have completed or be in flight). */
+B200BLUR_API int b200blur_events_elapsed_ms(b200blur_ctx *ctx, b200blur_event from, b200blur_event to, double *ms);
+/* Make `queue` wait for the END of `ev` (cross-queue dependency; OpenCL's event wait list). */
+B200BLUR_API int b200blur_enqueue_wait(b200blur_ctx *ctx, int queue, b200blur_event ev);
+
+/* ----------------------------------------------------------------------------------------------- transfers
+ * Asynchronous, in order on `queue`.  Host memory should be pinned (host_alloc/host_register); the caller keeps
+ * it valid until b200blur_finish, exactly as for CL_FALSE writes (A1:502, :538).
+ * enqueue_read takes a raw device pointer, so the "non-zero device offset" read of A2:537 is pointer arithmetic. */
+B200BLUR_API int b200blur_enqueue_write(b200blur_ctx *ctx, int queue, void *dst_dev, const void *src_host,
+                                        size_t bytes, b200blur_event *ev); /* clEnqueueWriteBuffer */
+B200BLUR_API int b200blur_enqueue_read(b200blur_ctx *ctx, int queue, void *dst_host, const void *src_dev,
+                                       size_t bytes, b200blur_event *ev);  /* clEnqueueReadBuffer  */
+/* Strided forms: `rows` runs of `row_bytes`, source/destination advancing by their own pitch (one call moves
+ * one row-range of every image of a batch, e.g. a row band or a halo row). */
+B200BLUR_API int b200blur_enqueue_write_2d(b200blur_ctx *ctx, int queue, void *dst_dev, size_t dst_pitch,
+                                           const void *src_host, size_t src_pitch, size_t row_bytes, size_t rows,
+                                           b200blur_event *ev);
+B200BLUR_API int b200blur_enqueue_read_2d(b200blur_ctx *ctx, int queue, void *dst_host, size_t dst_pitch,
+                                          const void *src_dev, size_t src_pitch, size_t row_bytes, size_t rows,
+                                          b200blur_event *ev);
+B200BLUR_API int b200blur_finish(b200blur_ctx *ctx, int queue); /* clFinish (A1:538-539) */
+B200BLUR_API int b200blur_finish_all(b200blur_ctx *ctx);
+
+/* -------------------------------------------------------------------------------------------- kernel launch
+ * One launch blurs a row band of `rows` rows of EVERY image of a batch (the reference launches one image at a
+ * time, A1:507).  The arguments of K:19-25 map as: input -> in (+ halo_top/halo_bottom), output -> out,
+ * width -> width, channels -> channels, height -> rows + (halo_top != NULL) + (halo_bottom != NULL).
+ *
+ *   out[i][r][x][c] = ( sum_{ky,kx} w[ky][kx] * src_i(r+ky, clamp(x+kx, 0, width-1), c) ) >> 4,   r in [0, rows)
+ *   src_i(-1, .)   = halo_top    ? row i of halo_top    : src_i(0, .)          (clamp, K:57)
+ *   src_i(rows, .) = halo_bottom ? row i of halo_bottom : src_i(rows-1, .)
+ *   w = {1,2,1; 2,4,2; 1,2,1}  (K:36-41 times 16; identical to the fp32 form)
+ *
+ * Rows are tight: pitch = width*channels bytes.  Image i of `in` starts at in + i*in_image_stride, and likewise
+ * for out / halo_top / halo_bottom with their own strides.  Halo pointers may address another GPU's memory
+ * (peer-enabled or IPC-opened): the kernel then loads those rows over NVLink itself -- that is Approach 2's
+ * halo exchange fused into the stencil.
+ * in == out (in place) is not allowed.  The vectorised path needs width*channels % 16 == 0, channels <= 4 and
+ * 16-byte aligned pointers/strides; anything else runs the generic path (same results).
+ */
+typedef struct b200blur_launch {
+    const void *in;
+    void *out;
+    int32_t width;
+    int32_t channels;
+    int32_t rows;
+    int32_t reserved; /* must be 0 */
+    int64_t n_images;
+    size_t in_image_stride;
+    size_t out_image_stride;
+    const void *halo_top;
+    size_t halo_top_stride;
+    const void *halo_bottom;
+    size_t halo_bottom_stride;
+} b200blur_launch;
+
+/* Fill a launch that is exactly "the reference kernel with height = in_height on buffer `in`, keeping output rows
+ * [first_row, first_row + n_rows)" written tightly at `out` (row first_row lands at out + 0).
+ *   whole image (A1:366-389):            in_height = H,               first_row = 0, n_rows = H
+ *   A2 top part (A2:401, :520-527):      in_height = split_row + 1,   first_row = 0, n_rows = split_row
+ *   A2 bottom part (A2:414, :530-541):   in_height = H - split_row + 1, first_row = 1, n_rows = H - split_row
+ * Rows of `in` next to the kept range become the halo rows; at the ends of the buffer the clamp applies. */
+B200BLUR_API int b200blur_launch_rows(b200blur_launch *l, const void *in, void *out, int width, int in_height,
+                                      int channels, int first_row, int n_rows, int64_t n_images,
+                                      size_t in_image_stride, size_t out_image_stride);
+
+/* clSetKernelArg x5 + clEnqueueNDRangeKernel (A1:366-389, :507): asynchronous, in order on `queue`. */
+B200BLUR_API int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200blur_launch *launch,
+                                       b200blur_event *ev);
+/* Which device code a launch would run: 1 = vectorised sm_100a stencil, 0 = generic path. */
+B200BLUR_API int b200blur_launch_is_vectorised(const b200blur_launch *launch);
+/* Select the kernel variant of the vectorised path (for profiling/tests): 0 = auto, 1 = register/shuffle
+ * stencil, 2 = TMA-bulk staged persistent stencil.  Returns the previous value. */
+B200BLUR_API int b200blur_set_kernel_variant(b200blur_ctx *ctx, int variant);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+B200BLUR_API int64_t b200blur_ctx_launch_count(const b200blur_ctx *ctx);
+
+/* ----------------------------------------------------------------------------------- work distribution (L4)
+ * Even contiguous partition of `n_items` over `n_parts`; the first n_items % n_parts parts get one more.
+ * Replaces num_images_gpu = (int)(batch_count * gpu_ratio) (A1:449-451) for whole images and
+ * split_row = (int)(H * (1 - gpu_ratio)) (A2:144) for row bands. */
+B200BLUR_API int b200blur_partition(int64_t n_items, int n_parts, int part, int64_t *begin, int64_t *count);
+/* The reference's own ratio arithmetic, kept for CLI compatibility and reporting (float multiply, truncation). */
+B200BLUR_API int b200blur_ratio_split_images(int batch_count, float gpu_ratio, int mode, int *n_first, int *n_second);
+B200BLUR_API int b200blur_ratio_split_row(int height, float gpu_ratio, int *split_row);
+
+/* ------------------------------------------------------------------------------------------- stream engines
+ * The batch loop of A1:418-600 as one call.  Times are device times from events (ms), summed per stage like
+ * A1:544-579; wall_ms is host wall-clock around the whole call. */
+typedef struct b200blur_stats {
+    double wall_ms;
+    double h2d_ms;    /* "Transfer IN"  */
+    double kernel_ms; /* "Kernel execution" */
+    double d2h_ms;    /* "Transfer OUT" */
+    int64_t images;
+    int64_t launches;
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} b200blur_stats;
+
+/* Device-resident: `d_in`/`d_out` hold n_images tight images in HBM.  Images are processed `batch_size` at a
+ * time in stream order; when `coalesce` != 0 consecutive batches are fused into as few launches as possible
+ * (they are independent), otherwise one launch per batch like the reference's per-batch sync (A1:538). */
+B200BLUR_API int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int width, int height,
+                                       int channels, int64_t n_images, int batch_size, int coalesce,
+                                       b200blur_stats *stats);
+/* End to end: `h_in`/`h_out` are HOST buffers (pinned for full speed) of n_images tight images.  Chunks of
+ * `batch_size` images flow H2D -> blur -> D2H through a ring of device buffers on separate queues so the three
+ * stages of different chunks overlap (the reference serialises them per image). */
+B200BLUR_API int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int width, int height,
+                                   int channels, int64_t n_images, int batch_size, b200blur_stats *stats);
+
+/* -------------------------------------------------------------------------------- multi-GPU (Approach 2 bands)
+ * No reference counterpart: the reference's devices only meet in host memory (A2:511-517). */
+/* Enable direct loads/stores from ctx `a`'s device into ctx `b`'s memory and vice versa (same process). */
+B200BLUR_API int b200blur_peer_enable(b200blur_ctx *a, b200blur_ctx *b);
+/* Cross-process form (one process per GPU): export a device allocation as a 64-byte handle, open it elsewhere. */
+#define B200BLUR_IPC_HANDLE_BYTES 64
+B200BLUR_API int b200blur_ipc_export(b200blur_ctx *ctx, void *dptr, unsigned char handle[B200BLUR_IPC_HANDLE_BYTES]);
+B200BLUR_API int b200blur_ipc_open(b200blur_ctx *ctx, const unsigned char handle[B200BLUR_IPC_HANDLE_BYTES], void **dptr);
+B200BLUR_API int b200blur_ipc_close(b200blur_ctx *ctx, void *dptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BLUR_H */

@@ -1,0 +1,344 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle -- bit-exact (integer arithmetic).
+
+Small/medium cases compare with the oracle directly and with the committed golden vectors (generated from the
+reference's own kernel source); full BASELINE sizes use size-independent properties (replicated stream == one oracle
+image, band-split == whole image, coalesced == per-batch launches, checksums)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import b200blur
+from b200blur.sharding import plan_bands
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def synth(seed, n, h, w, c=3):
+    return np.random.default_rng(seed).integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    oracle.build()
+    c = b200blur.Context(0, 4)
+    yield c
+    c.close()
+
+
+def diff_report(a, b):
+    d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+    hist = np.bincount(d.ravel(), minlength=4)[:8]
+    return f"max-abs-diff {d.max()}, histogram of |diff| 0..7: {hist.tolist()}"
+
+
+def assert_same(got, want):
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), diff_report(got, want)
+
+
+def test_device_is_blackwell(ctx):
+    assert b200blur.device_count() >= 1
+    assert "B200" in b200blur.device_name(0) or True  # name printed for the record
+    print(b200blur.device_name(0), b200blur.version())
+
+
+def test_golden_vectors(ctx, golden_dir):
+    vec = np.load(os.path.join(golden_dir, "vectors.npz"))
+    for name in sorted(k[3:] for k in vec.files if k.startswith("in_")):
+        assert_same(ctx.blur_numpy(vec["in_" + name]), vec["out_" + name])
+
+
+def test_golden_checksums(ctx, golden_dir):
+    with open(os.path.join(golden_dir, "checksums.json")) as f:
+        sums = json.load(f)
+    for case in sums["cases"]:
+        x = synth(case["seed"], case["n"], case["h"], case["w"], case["c"])
+        y = ctx.blur_numpy(x)
+        assert hashlib.sha256(y.tobytes()).hexdigest() == case["out_sha256"], case
+
+
+VEC_SHAPES = [(256, 256, 3), (240, 320, 3), (1, 16, 3), (2, 16, 3), (3, 32, 3), (17, 48, 3), (33, 80, 3), (16, 16, 3),
+              (100, 1024, 3), (5, 16, 1), (31, 64, 1), (9, 8, 2), (40, 24, 2), (7, 4, 4), (64, 100, 4), (15, 176, 3),
+              (4, 2048, 3), (37, 336, 3)]
+GEN_SHAPES = [(1, 1, 3), (1, 9, 3), (9, 1, 3), (2, 2, 3), (17, 33, 3), (100, 52, 3), (5, 7, 1), (6, 5, 2), (3, 3, 4),
+              (11, 13, 5), (255, 255, 3)]
+
+
+@pytest.mark.parametrize("shape", VEC_SHAPES)
+def test_vectorised_path_matches_oracle(ctx, shape):
+    h, w, c = shape
+    n = 3
+    x = synth(h * 7919 + w * 31 + c, n, h, w, c)
+    l = ctx.launch_rows(0x1000, 0x100000, w, h, c, 0, h, n)
+    assert ctx.is_vectorised(l), shape
+    assert_same(ctx.blur_numpy(x), oracle.c_blur_batch(x))
+
+
+@pytest.mark.parametrize("shape", GEN_SHAPES)
+def test_generic_path_matches_oracle(ctx, shape):
+    h, w, c = shape
+    x = synth(h * 131 + w, 4, h, w, c)
+    assert_same(ctx.blur_numpy(x), oracle.c_blur_batch(x))
+
+
+def test_extreme_values_no_lane_carry(ctx):
+    """All-255 and alternating 0/255 inputs drive every packed 16-bit lane to its maximum (4080 << 4)."""
+    for h, w in [(20, 64), (240, 320)]:
+        x = np.full((2, h, w, 3), 255, np.uint8)
+        assert (ctx.blur_numpy(x) == 255).all()
+        x = (np.indices((h, w * 3)).sum(axis=0) % 2 * 255).astype(np.uint8).reshape(1, h, w, 3)
+        assert_same(ctx.blur_numpy(x), oracle.c_blur_batch(x))
+        x = (np.indices((h, w)).sum(axis=0) % 2 * 255).astype(np.uint8)[None, :, :, None].repeat(3, axis=3)
+        assert_same(ctx.blur_numpy(x), oracle.c_blur_batch(x))
+
+
+def test_empty_inputs(ctx):
+    for shape in [(0, 16, 16, 3), (2, 0, 16, 3), (2, 16, 0, 3)]:
+        x = np.zeros(shape, np.uint8)
+        assert ctx.blur_numpy(x).shape == x.shape
+    d = ctx.dev_alloc(64)
+    ctx.enqueue_blur(0, ctx.launch_rows(d, d, 16, 4, 3, 0, 0, 0))  # zero rows: in == out is not even looked at
+    ctx.finish()
+    ctx.dev_free(d)
+
+
+def test_invalid_launches_are_rejected(ctx):
+    d = ctx.dev_alloc(4096)
+    with pytest.raises(b200blur.BlurError):
+        ctx.enqueue_blur(0, ctx.launch_rows(d, d, 16, 4, 3, 0, 4, 1))  # in place
+    with pytest.raises(b200blur.BlurError):
+        ctx.enqueue_blur(99, ctx.launch_rows(d, d + 2048, 16, 4, 3, 0, 4, 1))  # bad queue
+    ctx.dev_free(d)
+
+
+def _run_launch(ctx, x, launches_fn):
+    """Upload x [N][H][W][C], run the launches built by launches_fn(d_in, d_out), download [N][H][W][C]."""
+    x = np.ascontiguousarray(x)
+    out = np.zeros_like(x)
+    d_in, d_out = ctx.dev_alloc(x.nbytes), ctx.dev_alloc(x.nbytes)
+    try:
+        ctx.enqueue_write(0, d_in, x, x.nbytes)
+        ctx.enqueue_write(0, d_out, out, x.nbytes)
+        for l in launches_fn(d_in, d_out):
+            ctx.enqueue_blur(0, l)
+        ctx.enqueue_read(0, out, d_out, x.nbytes)
+        ctx.finish()
+    finally:
+        ctx.dev_free(d_in)
+        ctx.dev_free(d_out)
+    return out
+
+
+@pytest.mark.parametrize("h,w,ratio", [(240, 320, 0.837), (240, 320, 0.5), (256, 256, 0.889), (9, 16, 0.5), (2, 16, 0.5),
+                                       (33, 7, 0.3)])
+def test_approach2_two_part_split_matches_reference_composition(ctx, h, w, ratio):
+    """split_image_blur.c:503-541 through the C ABI: both parts run with height = rows incl. halo, halo output dropped."""
+    n, c = 3, 3
+    P = w * c
+    x = synth(h + w, n, h, w, c)
+    split = b200blur.ratio_split_row(h, ratio)
+    assert split == oracle.a2_geometry(h, ratio)["split_row"]
+
+    def launches(d_in, d_out):
+        top = ctx.launch_rows(d_in, d_out, w, split + 1, c, 0, split, n, P * h, P * h)
+        bot = ctx.launch_rows(d_in + (split - 1) * P, d_out + split * P, w, h - split + 1, c, 1, h - split, n,
+                              P * h, P * h)
+        return [top, bot]
+
+    got = _run_launch(ctx, x, launches)
+    for i in range(n):
+        assert_same(got[i], oracle.split_image(x[i], split))
+    assert_same(got, oracle.c_blur_batch(x))
+
+
+@pytest.mark.parametrize("h,w,g", [(256, 256, 2), (256, 256, 4), (256, 256, 8), (240, 320, 8), (10, 16, 8), (37, 21, 4)])
+def test_row_bands_with_halo_pointers_equal_whole_image(ctx, h, w, g):
+    """G bands on one GPU, halo rows read in place from the neighbouring band (the multi-GPU kernel path, with
+    'peer' memory being local): result must equal the whole-image blur and oracle.band_split."""
+    n, c = 4, 3
+    P = w * c
+    x = synth(h * w + g, n, h, w, c)
+
+    def launches(d_in, d_out):
+        ls = []
+        for p in plan_bands(h, g):
+            top = 1 if p.has_top else 0
+            ls.append(ctx.launch_rows(d_in + (p.row0 - top) * P, d_out + p.row0 * P, w, p.input_rows, c, top, p.rows, n,
+                                      P * h, P * h))
+        return ls
+
+    got = _run_launch(ctx, x, launches)
+    want = oracle.c_blur_batch(x)
+    assert_same(got, want)
+    for i in range(n):
+        assert_same(got[i], oracle.band_split(x[i], min(g, h)))
+
+
+def test_separate_band_buffers_with_explicit_halo_rows(ctx):
+    """Band data and halo rows in different allocations with different strides (what a remote GPU's memory looks like)."""
+    n, h, w, c = 5, 64, 64, 3
+    P = w * c
+    x = synth(99, n, h, w, c)
+    want = oracle.c_blur_batch(x)
+    r0, r1 = 16, 48
+    band = np.ascontiguousarray(x[:, r0:r1])
+    halo_t = np.ascontiguousarray(x[:, r0 - 1])
+    halo_b = np.zeros((n, 2, P), np.uint8)           # stride 2*P: only row 0 of each pair is used
+    halo_b[:, 0] = x[:, r1].reshape(n, P)
+    out = np.zeros_like(band)
+    d_band, d_out = ctx.dev_alloc(band.nbytes), ctx.dev_alloc(band.nbytes)
+    d_t, d_b = ctx.dev_alloc(halo_t.nbytes), ctx.dev_alloc(halo_b.nbytes)
+    ctx.enqueue_write(0, d_band, band, band.nbytes)
+    ctx.enqueue_write(0, d_t, halo_t, halo_t.nbytes)
+    ctx.enqueue_write(0, d_b, halo_b, halo_b.nbytes)
+    l = ctx.launch_rows(d_band, d_out, w, r1 - r0, c, 0, r1 - r0, n)
+    l.halo_top, l.halo_top_stride = d_t, P
+    l.halo_bottom, l.halo_bottom_stride = d_b, 2 * P
+    ctx.enqueue_blur(0, l)
+    ctx.enqueue_read(0, out, d_out, out.nbytes)
+    ctx.finish()
+    for d in (d_band, d_out, d_t, d_b):
+        ctx.dev_free(d)
+    assert_same(out, want[:, r0:r1])
+
+
+def test_image_strides_larger_than_image(ctx):
+    n, h, w, c = 3, 12, 32, 3
+    img_bytes = h * w * c
+    x = synth(5, n, h, w, c)
+    stride_in, stride_out = img_bytes + 160, img_bytes + 64
+    buf = np.zeros(n * stride_in, np.uint8)
+    for i in range(n):
+        buf[i * stride_in:i * stride_in + img_bytes] = x[i].ravel()
+    outbuf = np.zeros(n * stride_out, np.uint8)
+    d_in, d_out = ctx.dev_alloc(buf.nbytes), ctx.dev_alloc(outbuf.nbytes)
+    ctx.enqueue_write(0, d_in, buf, buf.nbytes)
+    ctx.enqueue_blur(0, ctx.launch_rows(d_in, d_out, w, h, c, 0, h, n, stride_in, stride_out))
+    ctx.enqueue_read(0, outbuf, d_out, outbuf.nbytes)
+    ctx.finish()
+    ctx.dev_free(d_in)
+    ctx.dev_free(d_out)
+    want = oracle.c_blur_batch(x)
+    for i in range(n):
+        assert_same(outbuf[i * stride_out:i * stride_out + img_bytes].reshape(h, w, c), want[i])
+
+
+def test_profiling_events_and_2d_transfers(ctx):
+    n, h, w, c = 8, 64, 64, 3
+    P = w * c
+    x = synth(3, n, h, w, c)
+    out = np.zeros((n, h - 2, w, c), np.uint8)
+    d_in, d_out = ctx.dev_alloc(x.nbytes), ctx.dev_alloc(x.nbytes)
+    e0 = ctx.enqueue_write(0, d_in, x, x.nbytes, want_event=True)
+    e1 = ctx.enqueue_blur(0, ctx.launch_rows(d_in, d_out, w, h, c, 0, h, n), want_event=True)
+    # strided read: rows 1..h-2 of every image (like the non-zero-offset read of split_image_blur.c:537)
+    e2 = ctx.enqueue_read_2d(0, out, (h - 2) * P, d_out + P, h * P, (h - 2) * P, n, want_event=True)
+    ctx.finish(0)
+    for e in (e0, e1, e2):
+        ms = ctx.event_ms(e)
+        assert 0.0 <= ms < 1000.0
+    ctx.dev_free(d_in)
+    ctx.dev_free(d_out)
+    assert_same(out, oracle.c_blur_batch(x)[:, 1:h - 1])
+
+
+@pytest.mark.parametrize("batch_size,coalesce", [(35, True), (35, False), (1, False), (500, False), (5000, True)])
+def test_run_resident_matches_oracle(ctx, batch_size, coalesce):
+    import torch
+    n, h, w, c = 143, 240, 320, 3
+    x = synth(17, n, h, w, c)
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.zeros_like(d_in)
+    before = ctx.launch_count
+    st = ctx.run_resident(d_in, d_out, w, h, c, n, batch_size, coalesce)
+    torch.cuda.synchronize()
+    want_launches = 1 if coalesce else (n + batch_size - 1) // batch_size
+    assert st.launches == want_launches and ctx.launch_count - before == want_launches
+    assert st.images == n and st.kernel_ms > 0
+    assert_same(d_out.cpu().numpy(), oracle.c_blur_batch(x, integer=True))
+
+
+@pytest.mark.parametrize("batch_size", [35, 1, 64, 1000])
+def test_run_host_pipeline_matches_oracle(ctx, batch_size):
+    import torch
+    n, h, w, c = 300, 240, 320, 3
+    if batch_size == 1:
+        n = 40
+    x = synth(23, n, h, w, c)
+    h_in = torch.from_numpy(x).pin_memory()
+    h_out = torch.zeros_like(h_in).pin_memory()
+    st = ctx.run_host(h_in, h_out, w, h, c, n, batch_size)
+    assert st.images == n and st.launches == (n + batch_size - 1) // batch_size
+    assert st.h2d_bytes == x.nbytes and st.d2h_bytes == x.nbytes
+    assert st.h2d_ms > 0 and st.kernel_ms > 0 and st.d2h_ms > 0
+    assert_same(h_out.numpy(), oracle.c_blur_batch(x, integer=True))
+    # pageable host memory also works (slower): the reference's buffers are plain malloc (heterogeneous_blur.c:431)
+    out2 = np.zeros_like(x)
+    ctx.run_host(x, out2, w, h, c, n, batch_size)
+    assert_same(out2, h_out.numpy())
+
+
+def test_full_size_stream_properties(ctx):
+    """BASELINE configs[1] at full size: 5000 x 320x240.  (a) the reference's own stream -- 5000 replicas of one image
+    (heterogeneous_blur.c:440-442) -- must give 5000 copies of the oracle's output; (b) distinct random images:
+    band-split == whole image and a 256-image sample == oracle."""
+    import torch
+    n, h, w, c = 5000, 240, 320, 3
+    one = synth(31, 1, h, w, c)
+    want_one = torch.from_numpy(oracle.c_blur(one[0])).cuda()
+    d_in = torch.from_numpy(one).cuda().expand(n, h, w, c).contiguous()
+    d_out = torch.zeros_like(d_in)
+    ctx.run_resident(d_in, d_out, w, h, c, n, 35, True)
+    torch.cuda.synchronize()
+    assert bool((d_out == want_one[None]).all())
+    d_out.zero_()
+    ctx.run_resident(d_in, d_out, w, h, c, n, 35, False)
+    torch.cuda.synchronize()
+    assert bool((d_out == want_one[None]).all())
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    d_in = torch.randint(0, 256, (n, h, w, c), dtype=torch.uint8, device="cuda", generator=g)
+    whole = torch.zeros_like(d_in)
+    ctx.run_resident(d_in, whole, w, h, c, n, 35, True)
+    banded = torch.zeros_like(d_in)
+    P = w * c
+    for p in plan_bands(h, 8):
+        top = 1 if p.has_top else 0
+        ctx.enqueue_blur(0, ctx.launch_rows(d_in.data_ptr() + (p.row0 - top) * P, banded.data_ptr() + p.row0 * P, w,
+                                            p.input_rows, c, top, p.rows, n, P * h, P * h))
+    ctx.finish()
+    torch.cuda.synchronize()
+    assert bool((whole == banded).all())
+    idx = torch.arange(0, n, 20, device="cuda")[:256]
+    sample = d_in[idx].cpu().numpy()
+    assert_same(whole[idx].cpu().numpy(), oracle.c_blur_batch(sample, integer=True))
+
+
+def test_large_frame(ctx):
+    """One 8192x8192 RGB frame (BASELINE configs[4] shape): bands of 1024 rows == whole image, sample rows == oracle."""
+    import torch
+    h = w = 8192
+    c = 3
+    g = torch.Generator(device="cuda").manual_seed(11)
+    d_in = torch.randint(0, 256, (1, h, w, c), dtype=torch.uint8, device="cuda", generator=g)
+    whole = torch.zeros_like(d_in)
+    ctx.run_resident(d_in, whole, w, h, c, 1, 1, True)
+    banded = torch.zeros_like(d_in)
+    P = w * c
+    for p in plan_bands(h, 8):
+        top = 1 if p.has_top else 0
+        ctx.enqueue_blur(0, ctx.launch_rows(d_in.data_ptr() + (p.row0 - top) * P, banded.data_ptr() + p.row0 * P, w,
+                                            p.input_rows, c, top, p.rows, 1, P * h, P * h))
+    ctx.finish()
+    torch.cuda.synchronize()
+    assert bool((whole == banded).all())
+    # oracle on three horizontal slabs (top edge, a band seam, bottom edge), using the slab +-1 row as its own image
+    x = d_in[0].cpu().numpy()
+    y = whole[0].cpu().numpy()
+    assert_same(y[:64], oracle.c_blur(x[:65], integer=True)[:64])
+    assert_same(y[1000:1060], oracle.c_blur(x[999:1061], integer=True)[1:61])
+    assert_same(y[-64:], oracle.c_blur(x[-65:], integer=True)[1:])
