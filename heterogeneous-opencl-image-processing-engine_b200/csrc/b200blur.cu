@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -60,8 +61,10 @@ struct b200blur_ctx {
     std::vector<cudaStream_t> queues;
     std::vector<EventSlot> events;
     std::vector<int> free_events;
-    int kernel_variant = 0;
+    int kernel_variant = 0;   // 0 auto, 1 register/shuffle strips, 2 TMA-bulk streamed
     int64_t launches = 0;
+    // tuning knobs of the streamed kernel (0 = automatic); set from B200BLUR_V2_* at context creation
+    int v2_threads = 0, v2_seg = 0, v2_cfg = 0, v2_ctas_per_sm = 0, v2_debug = 0;
     // ring of device buffers owned by b200blur_run_host
     struct Slot {
         uint8_t *d_in = nullptr, *d_out = nullptr;
@@ -187,13 +190,109 @@ void launch_strip(const b200blur::BandParams &p, cudaStream_t s, long long img0,
     }
 }
 
+using StreamKernel = void (*)(const b200blur::StreamParams);
+
+struct StreamCfg {
+    int rb, ns;
+    StreamKernel fn[4];  // by channels-1
+};
+
+template <int RB, int NS>
+constexpr StreamCfg make_cfg()
+{
+    return StreamCfg{RB, NS,
+                     {b200blur::blur_stream_kernel<1, RB, NS>, b200blur::blur_stream_kernel<2, RB, NS>,
+                      b200blur::blur_stream_kernel<3, RB, NS>, b200blur::blur_stream_kernel<4, RB, NS>}};
+}
+
+const StreamCfg kStreamCfgs[] = {make_cfg<8, 3>(), make_cfg<4, 3>(), make_cfg<4, 4>(), make_cfg<8, 4>(),
+                                 make_cfg<4, 6>(), make_cfg<16, 2>(), make_cfg<8, 2>()};
+constexpr int kNumStreamCfgs = sizeof(kStreamCfgs) / sizeof(kStreamCfgs[0]);
+
+// Whether the streamed (variant 2) kernel can run this launch: rows wide enough for bulk copies to pay.
+bool stream_eligible(const b200blur::BandParams &p) { return p.pitch >= 256; }
+
+int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s)
+{
+    b200blur::StreamParams sp;
+    sp.b = p;
+    sp.cpr = p.pitch / 16;
+    const StreamCfg &cfg = kStreamCfgs[(ctx->v2_cfg >= 0 && ctx->v2_cfg < kNumStreamCfgs) ? ctx->v2_cfg : 0];
+    int threads;
+    if (sp.cpr <= 256) {
+        // full-width rows: a CTA step covers `ipc` images side by side; pick the block size that wastes fewest lanes
+        sp.cb = sp.cpr;
+        sp.ncb = 1;
+        sp.margin = 0;
+        const int prefer = ctx->v2_threads > 0 ? ctx->v2_threads : 128;
+        int best_t = 0;
+        double best_score = -1.0;
+        for (int t = 64; t <= 256; t += 32) {
+            if (t < sp.cb) continue;
+            const int ipc = t / sp.cb;
+            const double eff = (double)(ipc * sp.cb) / t;
+            const double score = eff - 0.0005 * (t > prefer ? t - prefer : prefer - t);
+            if (score > best_score) { best_score = score; best_t = t; }
+        }
+        threads = best_t;
+        sp.ipc = threads / sp.cb;
+    } else {
+        threads = ctx->v2_threads > 0 ? ctx->v2_threads : 128;
+        if (threads > 256) threads = 256;
+        sp.cb = threads;
+        sp.ncb = (sp.cpr + sp.cb - 1) / sp.cb;
+        sp.margin = 16;
+        sp.ipc = 1;
+    }
+    sp.sstride = sp.cb * 16 + 2 * sp.margin;
+    sp.slot_bytes = sp.ipc * cfg.rb * sp.sstride;
+    const size_t smem = 16 + (size_t)cfg.ns * sp.slot_bytes + 16 + 16 * cfg.ns;
+    const int block = threads + 32;  // + the producer warp
+    if (smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", smem);
+    StreamKernel fn = cfg.fn[p.channels - 1];
+    if (ctx->v2_debug == 1 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 1>;
+    if (ctx->v2_debug == 2 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 2>;
+    if (ctx->v2_debug == 3 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 3>;
+    if (ctx->v2_debug == 4 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 4>;
+    if (ctx->v2_debug == 5 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 5>;
+    if (ctx->v2_debug == 6 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 6>;
+    if (ctx->v2_debug == 7 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 7>;
+    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
+    if (per_sm < 1) return fail(B200BLUR_ERR_CUDA, "streamed kernel does not fit on an SM");
+    if (ctx->v2_ctas_per_sm > 0 && per_sm > ctx->v2_ctas_per_sm) per_sm = ctx->v2_ctas_per_sm;
+    const long long slots = (long long)ctx->sm_count * per_sm;
+    sp.img_blocks = (p.n_images + sp.ipc - 1) / sp.ipc;
+    // segment height: whole band when there are plenty of images, shorter segments to fill the machine otherwise
+    int seg = p.rows;
+    if (ctx->v2_seg > 0) {
+        seg = ctx->v2_seg < p.rows ? ctx->v2_seg : p.rows;
+    } else {
+        while (seg > 32 && sp.img_blocks * sp.ncb * ((p.rows + seg - 1) / seg) < 4 * slots) seg = (seg + 1) / 2;
+    }
+    sp.seg = seg;
+    sp.nseg = (p.rows + seg - 1) / seg;
+    sp.n_groups = sp.img_blocks * sp.nseg * sp.ncb;
+    // Balanced persistent grid: every CTA gets the same number of groups (+-1), so no CTA is left running a last
+    // partial round alone while HBM idles.
+    const long long rounds = (sp.n_groups + slots - 1) / slots;
+    const long long grid = (sp.n_groups + rounds - 1) / rounds;
+    fn<<<(unsigned)grid, block, smem, s>>>(sp);
+    return B200BLUR_OK;
+}
+
 // Launches the device code for one b200blur_launch on stream s.  Returns the number of kernels launched.
 int do_launch(b200blur_ctx *ctx, cudaStream_t s, const b200blur_launch *l, int *n_kernels)
 {
     *n_kernels = 0;
     if (l->width == 0 || l->rows == 0 || l->n_images == 0) return B200BLUR_OK;  // nothing to do
     b200blur::BandParams p = to_params(l);
-    if (launch_vectorised(l)) {
+    const bool vec = launch_vectorised(l);
+    if (vec && stream_eligible(p) && ctx->kernel_variant != 1) {
+        if (int rc = launch_stream(ctx, p, s)) return rc;
+        ++*n_kernels;
+    } else if (vec) {
         // strip height: tall strips amortise the two halo rows; short strips expose more threads for small batches
         const long long cpr = p.pitch / 16;
         const long long threads_rs16 = cpr * ((p.rows + 15) / 16) * p.n_images;
@@ -289,6 +388,13 @@ int b200blur_ctx_create(int device, int n_queues, b200blur_ctx **out)
         return fail(B200BLUR_ERR_CUDA, "%d - cudaGetDeviceProperties: %s", (int)e, cudaGetErrorString(e));
     }
     ctx->sm_count = prop.multiProcessorCount;
+    auto env_int = [](const char *name) { const char *v = getenv(name); return v ? atoi(v) : 0; };
+    ctx->kernel_variant = env_int("B200BLUR_VARIANT");
+    ctx->v2_threads = env_int("B200BLUR_V2_THREADS");
+    ctx->v2_seg = env_int("B200BLUR_V2_SEG");
+    ctx->v2_cfg = env_int("B200BLUR_V2_CFG");
+    ctx->v2_ctas_per_sm = env_int("B200BLUR_V2_CTAS");
+    ctx->v2_debug = env_int("B200BLUR_V2_DEBUG");
     for (int i = 0; i < n_queues; i++) {
         cudaStream_t s;
         e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);

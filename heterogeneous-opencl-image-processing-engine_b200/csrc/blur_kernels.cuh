@@ -90,6 +90,19 @@ __device__ __forceinline__ void hpass(const uint4 &w, uint32_t wl, uint32_t wr, 
     }
 }
 
+// Same horizontal pass, results interleaved as h[2k] = E lanes, h[2k+1] = O lanes of word k.
+template <int C>
+__device__ __forceinline__ void hpass8(const uint4 &w, uint32_t wl, uint32_t wr, uint32_t (&h)[8])
+{
+    uint32_t hE[4], hO[4];
+    hpass<C>(w, wl, wr, hE, hO);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        h[2 * k] = hE[k];
+        h[2 * k + 1] = hO[k];
+    }
+}
+
 // Vertical [1 2 1] + >>4 + re-interleave: one output word from the h lanes of three rows.
 __device__ __forceinline__ uint32_t vpass_word(uint32_t upE, uint32_t midE, uint32_t dnE,
                                                uint32_t upO, uint32_t midO, uint32_t dnO)
@@ -181,6 +194,264 @@ blur_strip_kernel(const BandParams p, int cpr, int n_strips)
         for (int i = 0; i < 4; i++) {
             h2E[i] = h1E[i]; h2O[i] = h1O[i];
             h1E[i] = hE[i];  h1O[i] = hO[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ variant 2: TMA-bulk streamed persistent stencil
+// The Blackwell-native form.  Persistent CTAs (a few per SM) each stream "items" -- a segment of `seg` output rows of
+// a column block of `ipc` consecutive images -- through a ring of NS shared-memory slots.  One elected thread feeds
+// the ring with 1-D bulk async copies (cp.async.bulk global->shared, completion on an mbarrier; SASS UBLKCP): because
+// a small frame's rows are contiguous in memory, RB rows of an image arrive as ONE bulk copy; wide frames use one
+// bulk copy per row of a 2 KB column block (+16 B margins).  All threads then read their 16-byte chunk and the two
+// neighbouring words from shared memory (no shuffles, no edge lanes), keep the rolling horizontal sums of the two
+// previous rows in registers across slots, and emit one coalesced 16-byte store per output row.  In-flight bytes are
+// held by the ring (NS-1 slots per CTA), not by registers, and a segment re-reads only 2 halo rows per `seg` rows.
+// Halo rows above/below the band come from halo_top/halo_bot -- possibly another GPU's memory (NVLink) -- or are the
+// replicated edge row (gaussian_kernel.cl:57).
+struct StreamParams {
+    BandParams b;
+    int cpr;            // 16-byte chunks per row
+    int cb;             // chunks per column block (<= blockDim.x)
+    int ncb;            // column blocks per row
+    int ipc;            // images side by side in one CTA step (ncb == 1 only)
+    int seg;            // output rows per item
+    int nseg;           // segments per band
+    int margin;         // 0 (full-width rows, contiguous copies) or 16 (column blocks, per-row copies)
+    int sstride;        // shared-memory row stride in bytes = cb*16 + 2*margin
+    int slot_bytes;     // ipc * RB * sstride
+    long long img_blocks;   // ceil(n_images / ipc)
+    long long n_groups;     // img_blocks * nseg * ncb
+};
+
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion (bytes) signalled on an mbarrier.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+}  // namespace ptx
+
+// Decodes group index -> geometry.  Groups are ordered image-block major, then segment, then column block, so CTAs
+// that run concurrently work on adjacent segments of the same images and the shared halo rows hit in L2.
+struct GroupGeom {
+    long long img0;   // first image of the group
+    int n_img;        // images in the group (<= ipc)
+    int r0;           // first output row
+    int nr;           // output rows
+    int x0;           // first byte column of the column block
+    int cbe;          // chunks in this column block
+    bool left_edge, right_edge;
+};
+__device__ __forceinline__ GroupGeom decode_group(const StreamParams &sp, long long g)
+{
+    GroupGeom q;
+    const int per_block = sp.nseg * sp.ncb;
+    const long long ib = g / per_block;
+    const int sc = (int)(g - ib * per_block);
+    const int si = sc / sp.ncb;
+    const int ci = sc - si * sp.ncb;
+    q.img0 = ib * sp.ipc;
+    const long long left = sp.b.n_images - q.img0;
+    q.n_img = left < sp.ipc ? (int)left : sp.ipc;
+    q.r0 = si * sp.seg;
+    q.nr = min(sp.seg, sp.b.rows - q.r0);
+    q.x0 = ci * sp.cb * 16;
+    q.cbe = min(sp.cb, sp.cpr - ci * sp.cb);
+    q.left_edge = (ci == 0);
+    q.right_edge = (ci == sp.ncb - 1);
+    return q;
+}
+
+template <int RB>
+__device__ __forceinline__ void stream_issue_slot(const StreamParams &sp, const GroupGeom &q, int slot_in_item,
+                                                  uint32_t slot_smem, uint32_t bar)
+{
+    const BandParams &b = sp.b;
+    const int k0 = slot_in_item * RB;               // first input-row index of the slot within the item
+    const int k1 = min(k0 + RB, q.nr + 2);          // one past the last
+    // byte range of a row that this column block needs (margins clipped at the image edges)
+    const int lm = q.left_edge ? 0 : sp.margin;
+    const int rm = q.right_edge ? 0 : sp.margin;
+    const int xb = q.x0 - lm;
+    const uint32_t row_bytes = (uint32_t)(q.cbe * 16 + lm + rm);
+    const uint32_t dst_col = (uint32_t)(sp.margin - lm);
+    for (int il = 0; il < q.n_img; il++) {
+        const size_t img = (size_t)(q.img0 + il);
+        const uint8_t *src = b.in + img * b.in_stride;
+        const uint32_t dst_img = slot_smem + (uint32_t)(il * RB * sp.sstride);
+        int k = k0;
+        while (k < k1) {
+            const int j = q.r0 - 1 + k;  // input row relative to the band
+            const uint8_t *rp;
+            int run = 1;
+            if (j < 0) {
+                rp = b.halo_top ? b.halo_top + img * b.top_stride : src;
+            } else if (j >= b.rows) {
+                rp = b.halo_bot ? b.halo_bot + img * b.bot_stride : src + (size_t)(b.rows - 1) * b.pitch;
+            } else {
+                rp = src + (size_t)j * b.pitch;
+                if (sp.margin == 0) run = min(k1 - k, b.rows - j);  // contiguous rows: one copy
+            }
+            const uint32_t bytes = (sp.margin == 0) ? (uint32_t)run * (uint32_t)b.pitch : row_bytes;
+            const uint32_t dst = dst_img + (uint32_t)((k - k0) * sp.sstride) + dst_col;
+            ptx::mbar_expect_tx(bar, bytes);
+            ptx::bulk_g2s(dst, rp + xb, bytes, bar);
+            k += run;
+        }
+    }
+    ptx::mbar_arrive(bar);
+}
+
+// Warp-specialised: warp 0 is the producer (one elected lane issues the bulk copies and never computes), warps 1..
+// are consumers.  full[NS] barriers carry the copies' byte counts; empty[NS] barriers collect one arrival per consumer
+// warp, so consumer warps never wait for each other -- only for data.
+template <int C, int RB, int NS, int DBG = 0>   // DBG (experiments only): 1 = copy instead of blur, 2 = default-policy stores
+__global__ void __launch_bounds__(32 + 256)
+blur_stream_kernel(const StreamParams sp)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // layout: [16 B pad][NS slots][16 B pad][NS full barriers][NS empty barriers]
+    const uint32_t ring = ptx::smem_u32(smem_raw) + 16;
+    const uint32_t full = ring + (uint32_t)(NS * sp.slot_bytes) + 16;
+    const uint32_t empty = full + 8 * NS;
+    const int t = threadIdx.x;
+    const int n_cwarps = (blockDim.x >> 5) - 1;
+    if (t == 0) {
+        for (int i = 0; i < NS; i++) {
+            ptx::mbar_init(full + 8 * i, 1);
+            ptx::mbar_init(empty + 8 * i, n_cwarps);
+        }
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (t < 32) {
+        // ------------------------------------------------------------------ producer warp
+        if (t == 0) {
+            unsigned pcount = 0;
+            for (long long g = blockIdx.x; g < sp.n_groups; g += gridDim.x) {
+                const GroupGeom q = decode_group(sp, g);
+                const int nslots = (q.nr + 2 + RB - 1) / RB;
+                for (int s = 0; s < nslots; s++, pcount++) {
+                    const int buf = pcount % NS;
+                    // wait until every consumer warp has released this buffer (passes at once on first use)
+                    if (DBG >= 4) continue;  // write-only experiments: no loads at all
+                    ptx::mbar_wait(empty + 8 * buf, ((pcount / NS) & 1) ^ 1);
+                    stream_issue_slot<RB>(sp, q, s, ring + (uint32_t)(buf * sp.slot_bytes), full + 8 * buf);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const int ct = t - 32;
+    const int il = ct / sp.cb;           // image lane within the group
+    const int c = ct - il * sp.cb;       // chunk within the column block
+    const int lane = t & 31;
+    unsigned ccount = 0;                 // slots consumed so far
+    for (long long g = blockIdx.x; g < sp.n_groups; g += gridDim.x) {
+        const GroupGeom q = decode_group(sp, g);
+        const bool active = (il < q.n_img) && (c < q.cbe);
+        const bool first = q.left_edge && (c == 0);
+        const bool last = q.right_edge && (c == q.cbe - 1);
+        const int nslots = (q.nr + 2 + RB - 1) / RB;
+        const int il_c = active ? il : 0, c_c = active ? c : 0;
+        const uint32_t lane_off = (uint32_t)(il_c * RB * sp.sstride + sp.margin + c_c * 16);
+        // Output row k-2 is produced when input row k of the item arrives; the store pointer starts two rows early
+        // and advances every row so the loop body has no branches (stores for k < 2 and k >= nr+2 are predicated off).
+        uint8_t *dst = sp.b.out + (size_t)(q.img0 + il_c) * sp.b.out_stride + (size_t)q.r0 * sp.b.pitch + q.x0 + c_c * 16 -
+                       2 * (ptrdiff_t)sp.b.pitch;
+        // Rolling vertical state, pre-scaled by 16: before row k arrives
+        //   accA = 16*(h[k-2] + 2*h[k-1])   accB = 16*h[k-1]        (<= 48960 per 16-bit lane)
+        uint32_t accA[8], accB[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) accA[i] = accB[i] = 0;
+        const int k_end = q.nr + 2;
+        int k = 0;  // input-row index within the item
+        for (int s = 0; s < nslots; s++, ccount++) {
+            const int buf = ccount % NS;
+            if (DBG < 4) ptx::mbar_wait(full + 8 * buf, (ccount / NS) & 1);
+            uint32_t a = ring + (uint32_t)(buf * sp.slot_bytes) + lane_off;
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                const uint4 w = ptx::lds128(a);
+                uint32_t wl = ptx::lds32(a - 4);
+                uint32_t wr = ptx::lds32(a + 16);
+                a += sp.sstride;
+                if (first) wl = w.x << (8 * (4 - C));   // clamp: pixel -1 := pixel 0        (gaussian_kernel.cl:56)
+                if (last) wr = w.w >> (8 * (4 - C));    // clamp: pixel width := pixel width-1
+                uint32_t h[8];
+                hpass8<C>(w, wl, wr, h);
+                uint32_t v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    v[i] = h[i] * 16u + accA[i];       // 16*(h[k-2] + 2*h[k-1] + h[k])  <= 65280 per lane
+                    accA[i] = h[i] * 32u + accB[i];
+                    accB[i] = h[i] << 4;
+                }
+                uint4 o;
+                o.x = __byte_perm(v[0], v[1], 0x7351);
+                o.y = __byte_perm(v[2], v[3], 0x7351);
+                o.z = __byte_perm(v[4], v[5], 0x7351);
+                o.w = __byte_perm(v[6], v[7], 0x7351);
+                if (DBG == 1 || DBG >= 3) o = w;
+                if (DBG == 3) {  // read-only experiment: keep the loads live, store (almost) never
+                    if (o.x == 0x12345678u && o.y == 0x9abcdef0u && o.z == 77u) stg128_stream(dst, o);
+                } else
+                if (active && k >= 2 && k < k_end) {
+                    if (DBG == 2 || DBG == 5) *reinterpret_cast<uint4 *>(dst) = o;
+                    else if (DBG == 6) __stcg(reinterpret_cast<uint4 *>(dst), o);
+                    else if (DBG == 7) __stwt(reinterpret_cast<uint4 *>(dst), o);
+                    else stg128_stream(dst, o);
+                }
+                dst += sp.b.pitch;
+                k++;
+            }
+            __syncwarp();
+            if (DBG < 4 && lane == 0) ptx::mbar_arrive(empty + 8 * buf);   // this warp is done reading the slot
         }
     }
 }

@@ -21,10 +21,13 @@ def synth(seed, n, h, w, c=3):
     return np.random.default_rng(seed).integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=[0, 1], ids=["auto-streamed", "strips"])
+def ctx(request):
+    """Every test runs against both vectorised kernel variants: 0 = automatic (the TMA-bulk streamed kernel wherever
+    rows are >= 256 bytes, the register/shuffle strip kernel below that), 1 = strip kernel everywhere."""
     oracle.build()
     c = b200blur.Context(0, 4)
+    c.set_kernel_variant(request.param)
     yield c
     c.close()
 
@@ -253,6 +256,7 @@ def test_run_resident_matches_oracle(ctx, batch_size, coalesce):
     x = synth(17, n, h, w, c)
     d_in = torch.from_numpy(x).cuda()
     d_out = torch.zeros_like(d_in)
+    torch.cuda.synchronize()  # torch's stream and the context's queues are independent
     before = ctx.launch_count
     st = ctx.run_resident(d_in, d_out, w, h, c, n, batch_size, coalesce)
     torch.cuda.synchronize()
@@ -292,10 +296,12 @@ def test_full_size_stream_properties(ctx):
     want_one = torch.from_numpy(oracle.c_blur(one[0])).cuda()
     d_in = torch.from_numpy(one).cuda().expand(n, h, w, c).contiguous()
     d_out = torch.zeros_like(d_in)
+    torch.cuda.synchronize()  # torch's stream and the context's queues are independent
     ctx.run_resident(d_in, d_out, w, h, c, n, 35, True)
     torch.cuda.synchronize()
     assert bool((d_out == want_one[None]).all())
     d_out.zero_()
+    torch.cuda.synchronize()
     ctx.run_resident(d_in, d_out, w, h, c, n, 35, False)
     torch.cuda.synchronize()
     assert bool((d_out == want_one[None]).all())
@@ -303,8 +309,9 @@ def test_full_size_stream_properties(ctx):
     g = torch.Generator(device="cuda").manual_seed(7)
     d_in = torch.randint(0, 256, (n, h, w, c), dtype=torch.uint8, device="cuda", generator=g)
     whole = torch.zeros_like(d_in)
-    ctx.run_resident(d_in, whole, w, h, c, n, 35, True)
     banded = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    ctx.run_resident(d_in, whole, w, h, c, n, 35, True)
     P = w * c
     for p in plan_bands(h, 8):
         top = 1 if p.has_top else 0
@@ -326,8 +333,9 @@ def test_large_frame(ctx):
     g = torch.Generator(device="cuda").manual_seed(11)
     d_in = torch.randint(0, 256, (1, h, w, c), dtype=torch.uint8, device="cuda", generator=g)
     whole = torch.zeros_like(d_in)
-    ctx.run_resident(d_in, whole, w, h, c, 1, 1, True)
     banded = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    ctx.run_resident(d_in, whole, w, h, c, 1, 1, True)
     P = w * c
     for p in plan_bands(h, 8):
         top = 1 if p.has_top else 0
