@@ -72,6 +72,8 @@ struct b200blur_ctx {
     };
     std::vector<Slot> ring;
     size_t ring_slot_bytes = 0;
+    // work counters of the streamed kernel: two 64-bit words per queue, zero between launches
+    unsigned long long *d_work = nullptr;
 };
 
 namespace {
@@ -212,7 +214,7 @@ constexpr int kNumStreamCfgs = sizeof(kStreamCfgs) / sizeof(kStreamCfgs[0]);
 // Whether the streamed (variant 2) kernel can run this launch: rows wide enough for bulk copies to pay.
 bool stream_eligible(const b200blur::BandParams &p) { return p.pitch >= 256; }
 
-int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s)
+int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s, int queue)
 {
     b200blur::StreamParams sp;
     sp.b = p;
@@ -246,17 +248,11 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
     }
     sp.sstride = sp.cb * 16 + 2 * sp.margin;
     sp.slot_bytes = sp.ipc * cfg.rb * sp.sstride;
-    const size_t smem = 16 + (size_t)cfg.ns * sp.slot_bytes + 16 + 16 * cfg.ns;
+    const size_t smem = 16 + (size_t)cfg.ns * sp.slot_bytes + 16 + 24 * cfg.ns;
     const int block = threads + 32;  // + the producer warp
     if (smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", smem);
     StreamKernel fn = cfg.fn[p.channels - 1];
     if (ctx->v2_debug == 1 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 1>;
-    if (ctx->v2_debug == 2 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 2>;
-    if (ctx->v2_debug == 3 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 3>;
-    if (ctx->v2_debug == 4 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 4>;
-    if (ctx->v2_debug == 5 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 5>;
-    if (ctx->v2_debug == 6 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 6>;
-    if (ctx->v2_debug == 7 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 7>;
     CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
@@ -264,33 +260,45 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
     if (ctx->v2_ctas_per_sm > 0 && per_sm > ctx->v2_ctas_per_sm) per_sm = ctx->v2_ctas_per_sm;
     const long long slots = (long long)ctx->sm_count * per_sm;
     sp.img_blocks = (p.n_images + sp.ipc - 1) / sp.ipc;
-    // segment height: whole band when there are plenty of images, shorter segments to fill the machine otherwise
-    int seg = p.rows;
+    // Work unit = `seg` output rows of `ipc` images (or of one column block): ~48 KB in + 48 KB out for full-width
+    // rows, ~128 KB for column blocks, and seg + 2 input rows fill whole slots ((seg + 2) % RB == 0).
+    int seg;
     if (ctx->v2_seg > 0) {
-        seg = ctx->v2_seg < p.rows ? ctx->v2_seg : p.rows;
+        seg = ctx->v2_seg;
     } else {
-        while (seg > 32 && sp.img_blocks * sp.ncb * ((p.rows + seg - 1) / seg) < 4 * slots) seg = (seg + 1) / 2;
+        const double unit_bytes = sp.ncb == 1 ? 48.0 * 1024 : 128.0 * 1024;
+        const double row_bytes = (double)sp.ipc * sp.cb * 16;
+        int m = (int)((unit_bytes / row_bytes + 2.0) / cfg.rb + 0.5);
+        if (m < 1) m = 1;
+        seg = m * cfg.rb - 2;
+        // few images: shorter units so that every SM gets several
+        while (seg > cfg.rb - 2 && sp.img_blocks * sp.ncb * ((p.rows + seg - 1) / seg) < 2 * slots) {
+            m = (m + 1) / 2;
+            seg = m * cfg.rb - 2;
+            if (m == 1) break;
+        }
+        if (seg < 2) seg = 2;
     }
+    if (seg > p.rows) seg = p.rows;
     sp.seg = seg;
     sp.nseg = (p.rows + seg - 1) / seg;
     sp.n_groups = sp.img_blocks * sp.nseg * sp.ncb;
-    // Balanced persistent grid: every CTA gets the same number of groups (+-1), so no CTA is left running a last
-    // partial round alone while HBM idles.
-    const long long rounds = (sp.n_groups + slots - 1) / slots;
-    const long long grid = (sp.n_groups + rounds - 1) / rounds;
+    sp.work = ctx->d_work + 2 * queue;
+    const long long grid = sp.n_groups < slots ? sp.n_groups : slots;
     fn<<<(unsigned)grid, block, smem, s>>>(sp);
     return B200BLUR_OK;
 }
 
 // Launches the device code for one b200blur_launch on stream s.  Returns the number of kernels launched.
-int do_launch(b200blur_ctx *ctx, cudaStream_t s, const b200blur_launch *l, int *n_kernels)
+int do_launch(b200blur_ctx *ctx, int queue, const b200blur_launch *l, int *n_kernels)
 {
+    cudaStream_t s = ctx->queues[queue];
     *n_kernels = 0;
     if (l->width == 0 || l->rows == 0 || l->n_images == 0) return B200BLUR_OK;  // nothing to do
     b200blur::BandParams p = to_params(l);
     const bool vec = launch_vectorised(l);
     if (vec && stream_eligible(p) && ctx->kernel_variant != 1) {
-        if (int rc = launch_stream(ctx, p, s)) return rc;
+        if (int rc = launch_stream(ctx, p, s, queue)) return rc;
         ++*n_kernels;
     } else if (vec) {
         // strip height: tall strips amortise the two halo rows; short strips expose more threads for small batches
@@ -405,6 +413,13 @@ int b200blur_ctx_create(int device, int n_queues, b200blur_ctx **out)
         }
         ctx->queues.push_back(s);
     }
+    e = cudaMalloc((void **)&ctx->d_work, sizeof(unsigned long long) * 2 * n_queues);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_work, 0, sizeof(unsigned long long) * 2 * n_queues);
+    if (e != cudaSuccess) {
+        for (auto q : ctx->queues) cudaStreamDestroy(q);
+        delete ctx;
+        return fail(B200BLUR_ERR_CUDA, "%d - work counter allocation: %s", (int)e, cudaGetErrorString(e));
+    }
     *out = ctx;
     return B200BLUR_OK;
 }
@@ -427,6 +442,7 @@ int b200blur_ctx_destroy(b200blur_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (auto q : ctx->queues) cudaStreamSynchronize(q);
     ring_release(ctx);
+    if (ctx->d_work) cudaFree(ctx->d_work);
     for (auto &e : ctx->events) {
         if (e.start) cudaEventDestroy(e.start);
         if (e.end) cudaEventDestroy(e.end);
@@ -680,7 +696,7 @@ int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200blur_launch *l
     int slot;
     if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
     int nk;
-    if (int rc = do_launch(ctx, ctx->queues[queue], launch, &nk)) return rc;
+    if (int rc = do_launch(ctx, queue, launch, &nk)) return rc;
     return event_end(ctx, queue, slot);
 }
 
@@ -750,7 +766,7 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
             return rc;
         if (int rc = launch_validate(&l)) return rc;
         int nk;
-        if (int rc = do_launch(ctx, s, &l, &nk)) return rc;
+        if (int rc = do_launch(ctx, 0, &l, &nk)) return rc;
         launches += nk;
     }
     if (stats) {
@@ -829,7 +845,7 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
                                           image_bytes))
             return rc;
         int nk;
-        if (int rc = do_launch(ctx, q_k, &l, &nk)) return rc;
+        if (int rc = do_launch(ctx, 1, &l, &nk)) return rc;
         launches += nk;
         CU_TRY(cudaEventRecord(s.ev[3], q_k));
         // D2H

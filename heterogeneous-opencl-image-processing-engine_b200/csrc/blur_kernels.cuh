@@ -222,6 +222,7 @@ struct StreamParams {
     int slot_bytes;     // ipc * RB * sstride
     long long img_blocks;   // ceil(n_images / ipc)
     long long n_groups;     // img_blocks * nseg * ncb
+    unsigned long long *work;  // work[0] = next group to hand out, work[1] = CTAs finished (both 0 between launches)
 };
 
 namespace ptx {
@@ -347,15 +348,19 @@ __device__ __forceinline__ void stream_issue_slot(const StreamParams &sp, const 
 // Warp-specialised: warp 0 is the producer (one elected lane issues the bulk copies and never computes), warps 1..
 // are consumers.  full[NS] barriers carry the copies' byte counts; empty[NS] barriers collect one arrival per consumer
 // warp, so consumer warps never wait for each other -- only for data.
-template <int C, int RB, int NS, int DBG = 0>   // DBG (experiments only): 1 = copy instead of blur, 2 = default-policy stores
+// Work is handed out dynamically: the producer takes the next group from a global atomic counter and publishes its
+// index next to the slot (meta[]), so SMs that see more bandwidth simply take more groups.  (A static round-robin
+// persistent grid loses ~10 % of HBM bandwidth on B200 -- tools/membench.cu, profiles/membench_r01.txt.)
+template <int C, int RB, int NS, int DBG = 0>   // DBG = 1 (experiments only): copy the rows instead of blurring them
 __global__ void __launch_bounds__(32 + 256)
 blur_stream_kernel(const StreamParams sp)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    // layout: [16 B pad][NS slots][16 B pad][NS full barriers][NS empty barriers]
+    // layout: [16 B pad][NS slots][16 B pad][NS full barriers][NS empty barriers][NS group indices]
     const uint32_t ring = ptx::smem_u32(smem_raw) + 16;
     const uint32_t full = ring + (uint32_t)(NS * sp.slot_bytes) + 16;
     const uint32_t empty = full + 8 * NS;
+    volatile long long *meta = reinterpret_cast<volatile long long *>(smem_raw + 16 + (size_t)NS * sp.slot_bytes + 16 + 16 * NS);
     const int t = threadIdx.x;
     const int n_cwarps = (blockDim.x >> 5) - 1;
     if (t == 0) {
@@ -371,16 +376,30 @@ blur_stream_kernel(const StreamParams sp)
         // ------------------------------------------------------------------ producer warp
         if (t == 0) {
             unsigned pcount = 0;
-            for (long long g = blockIdx.x; g < sp.n_groups; g += gridDim.x) {
-                const GroupGeom q = decode_group(sp, g);
-                const int nslots = (q.nr + 2 + RB - 1) / RB;
+            for (;;) {
+                const long long g = (long long)atomicAdd(sp.work, 1ull);
+                const bool done = g >= sp.n_groups;
+                GroupGeom q;
+                int nslots = 1;
+                if (!done) {
+                    q = decode_group(sp, g);
+                    nslots = (q.nr + 2 + RB - 1) / RB;
+                }
                 for (int s = 0; s < nslots; s++, pcount++) {
                     const int buf = pcount % NS;
                     // wait until every consumer warp has released this buffer (passes at once on first use)
-                    if (DBG >= 4) continue;  // write-only experiments: no loads at all
                     ptx::mbar_wait(empty + 8 * buf, ((pcount / NS) & 1) ^ 1);
-                    stream_issue_slot<RB>(sp, q, s, ring + (uint32_t)(buf * sp.slot_bytes), full + 8 * buf);
+                    if (s == 0) meta[buf] = done ? -1 : g;
+                    if (done) ptx::mbar_arrive(full + 8 * buf);   // sentinel slot: no data, tells the consumers to stop
+                    else stream_issue_slot<RB>(sp, q, s, ring + (uint32_t)(buf * sp.slot_bytes), full + 8 * buf);
                 }
+                if (done) break;
+            }
+            // the last CTA to run out of work re-arms the counters for the next launch on this queue
+            __threadfence();
+            if (atomicAdd(sp.work + 1, 1ull) == (unsigned long long)gridDim.x - 1) {
+                sp.work[0] = 0;
+                sp.work[1] = 0;
             }
         }
         return;
@@ -392,7 +411,11 @@ blur_stream_kernel(const StreamParams sp)
     const int c = ct - il * sp.cb;       // chunk within the column block
     const int lane = t & 31;
     unsigned ccount = 0;                 // slots consumed so far
-    for (long long g = blockIdx.x; g < sp.n_groups; g += gridDim.x) {
+    for (;;) {
+        // the first slot of an item carries the group index
+        ptx::mbar_wait(full + 8 * (ccount % NS), (ccount / NS) & 1);
+        const long long g = meta[ccount % NS];
+        if (g < 0) break;
         const GroupGeom q = decode_group(sp, g);
         const bool active = (il < q.n_img) && (c < q.cbe);
         const bool first = q.left_edge && (c == 0);
@@ -413,7 +436,7 @@ blur_stream_kernel(const StreamParams sp)
         int k = 0;  // input-row index within the item
         for (int s = 0; s < nslots; s++, ccount++) {
             const int buf = ccount % NS;
-            if (DBG < 4) ptx::mbar_wait(full + 8 * buf, (ccount / NS) & 1);
+            if (s > 0) ptx::mbar_wait(full + 8 * buf, (ccount / NS) & 1);
             uint32_t a = ring + (uint32_t)(buf * sp.slot_bytes) + lane_off;
 #pragma unroll
             for (int r = 0; r < RB; r++) {
@@ -437,21 +460,13 @@ blur_stream_kernel(const StreamParams sp)
                 o.y = __byte_perm(v[2], v[3], 0x7351);
                 o.z = __byte_perm(v[4], v[5], 0x7351);
                 o.w = __byte_perm(v[6], v[7], 0x7351);
-                if (DBG == 1 || DBG >= 3) o = w;
-                if (DBG == 3) {  // read-only experiment: keep the loads live, store (almost) never
-                    if (o.x == 0x12345678u && o.y == 0x9abcdef0u && o.z == 77u) stg128_stream(dst, o);
-                } else
-                if (active && k >= 2 && k < k_end) {
-                    if (DBG == 2 || DBG == 5) *reinterpret_cast<uint4 *>(dst) = o;
-                    else if (DBG == 6) __stcg(reinterpret_cast<uint4 *>(dst), o);
-                    else if (DBG == 7) __stwt(reinterpret_cast<uint4 *>(dst), o);
-                    else stg128_stream(dst, o);
-                }
+                if (DBG == 1) o = w;
+                if (active && k >= 2 && k < k_end) stg128_stream(dst, o);
                 dst += sp.b.pitch;
                 k++;
             }
             __syncwarp();
-            if (DBG < 4 && lane == 0) ptx::mbar_arrive(empty + 8 * buf);   // this warp is done reading the slot
+            if (lane == 0) ptx::mbar_arrive(empty + 8 * buf);   // this warp is done reading the slot
         }
     }
 }
