@@ -318,7 +318,7 @@ def run_b200_arm(args) -> None:
                        "l2": "inputs larger than L2 (1.15 GB in + 1.15 GB out per step vs 126 MB L2)",
                        "kernel_variant": args.variant, "parity_vs_oracle": parity},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "blur_strip_kernel<3,16>",
+                         "traffic": traffic, "kernel": "blur_stream_kernel<3,8,4> (TMA-bulk streamed stencil)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_IMAGE * images_per_launch,
                          "launch_ms": launch_ms, "peak_source": peak_note, "frac_of_nominal_8000": achieved / 8000.0},
             "cpu_baseline": cpu,

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "b200blur_enqueue_marker": (c_int, [c_void_p, c_int, POINTER(c_int32)]),
     "b200blur_events_elapsed_ms": (c_int, [c_void_p, c_int32, c_int32, POINTER(c_double)]),
     "b200blur_enqueue_wait": (c_int, [c_void_p, c_int, c_int32]),
+    "b200blur_enqueue_wait_peer": (c_int, [c_void_p, c_int, c_void_p, c_int32]),
     "b200blur_enqueue_write": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_int32)]),
     "b200blur_enqueue_read": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_int32)]),
     "b200blur_enqueue_write_2d": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t,
@@ -284,6 +285,9 @@ class Context:
 
     def enqueue_wait(self, queue, ev) -> None:
         _check(self._lib.b200blur_enqueue_wait(self._h, queue, ev))
+
+    def enqueue_wait_peer(self, queue, src: "Context", ev) -> None:
+        _check(self._lib.b200blur_enqueue_wait_peer(self._h, queue, src._h, ev))
 
     def finish(self, queue=None) -> None:
         if queue is None:

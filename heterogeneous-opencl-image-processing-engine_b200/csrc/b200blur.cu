@@ -207,7 +207,8 @@ constexpr StreamCfg make_cfg()
                       b200blur::blur_stream_kernel<3, RB, NS>, b200blur::blur_stream_kernel<4, RB, NS>}};
 }
 
-const StreamCfg kStreamCfgs[] = {make_cfg<8, 3>(), make_cfg<4, 3>(), make_cfg<4, 4>(), make_cfg<8, 4>(),
+// {rows per slot, slots}; index 0 is the default (B200BLUR_V2_CFG selects another for tuning runs)
+const StreamCfg kStreamCfgs[] = {make_cfg<8, 4>(), make_cfg<8, 3>(), make_cfg<4, 3>(), make_cfg<4, 4>(),
                                  make_cfg<4, 6>(), make_cfg<16, 2>(), make_cfg<8, 2>()};
 constexpr int kNumStreamCfgs = sizeof(kStreamCfgs) / sizeof(kStreamCfgs[0]);
 
@@ -252,7 +253,7 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
     const int block = threads + 32;  // + the producer warp
     if (smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", smem);
     StreamKernel fn = cfg.fn[p.channels - 1];
-    if (ctx->v2_debug == 1 && p.channels == 3) fn = b200blur::blur_stream_kernel<3, 8, 4, 1>;
+    if (ctx->v2_debug == 1 && p.channels == 3 && cfg.rb == 8 && cfg.ns == 4) fn = b200blur::blur_stream_kernel<3, 8, 4, 1>;
     CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
@@ -578,6 +579,17 @@ int b200blur_enqueue_wait(b200blur_ctx *ctx, int queue, b200blur_event ev)
         return fail(B200BLUR_ERR_INVALID, "event %d is not live", (int)ev);
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaStreamWaitEvent(ctx->queues[queue], ctx->events[ev].end, 0));
+    return B200BLUR_OK;
+}
+
+int b200blur_enqueue_wait_peer(b200blur_ctx *ctx, int queue, b200blur_ctx *src, b200blur_event ev)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    if (int rc = ctx_check(src)) return rc;
+    if (ev < 0 || ev >= (int)src->events.size() || !src->events[ev].in_use)
+        return fail(B200BLUR_ERR_INVALID, "event %d is not live in the source context", (int)ev);
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaStreamWaitEvent(ctx->queues[queue], src->events[ev].end, 0));
     return B200BLUR_OK;
 }
 

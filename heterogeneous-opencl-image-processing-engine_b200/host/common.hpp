@@ -1,0 +1,163 @@
+// common.hpp -- shared host-side pieces of the two drop-in CLIs (heterogeneous_blur, split_image_blur).
+//
+// Everything here is plain C++ over the C ABI in include/b200blur.h; there is no CUDA, PyTorch or OpenCL in the host
+// programs.  Mirrors the helper layer the reference keeps inline in main(): cl_error (heterogeneous_blur.c:25-30),
+// get_time_ms (:32-36), the image load + planar->interleaved step (:106-135) and save_one_image_rgb
+// (split_image_blur.c:40-56).
+#pragma once
+#include <sys/time.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b200blur.h"
+
+// cl_error(): print "<code> - <message>" and exit(-1), the reference's only error path for device calls.
+inline void blur_check(int code, const char *what)
+{
+    if (code != B200BLUR_OK) {
+        printf("%d - %s (%s)\n", code, what, b200blur_last_error());
+        exit(-1);
+    }
+}
+
+inline double get_time_ms()
+{
+    struct timeval tv;
+    gettimeofday(&tv, NULL);
+    return (tv.tv_sec * 1000.0) + (tv.tv_usec / 1000.0);
+}
+
+struct Image {
+    int width = 0, height = 0, channels = 3;
+    std::vector<unsigned char> data;  // interleaved RGBRGB..., the layout the kernel takes (heterogeneous_blur.c:128-135)
+    size_t size() const { return (size_t)width * height * channels; }
+};
+
+// Binary PPM (P6, maxval 255) reader: the dependency-free stand-in for CImg + libjpeg.
+inline bool load_ppm(const char *path, Image &img)
+{
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return false;
+    auto next_int = [&](int &v) -> bool {
+        int c = fgetc(fp);
+        while (c == ' ' || c == '\n' || c == '\r' || c == '\t' || c == '#') {
+            if (c == '#') while (c != '\n' && c != EOF) c = fgetc(fp);
+            c = fgetc(fp);
+        }
+        if (c < '0' || c > '9') return false;
+        v = 0;
+        while (c >= '0' && c <= '9') { v = v * 10 + (c - '0'); c = fgetc(fp); }
+        return true;
+    };
+    char magic[3] = {0, 0, 0};
+    if (fread(magic, 1, 2, fp) != 2 || magic[0] != 'P' || magic[1] != '6') { fclose(fp); return false; }
+    int w, h, maxval;
+    if (!next_int(w) || !next_int(h) || !next_int(maxval) || maxval != 255 || w <= 0 || h <= 0) { fclose(fp); return false; }
+    img.width = w; img.height = h; img.channels = 3;
+    img.data.resize(img.size());
+    const bool ok = fread(img.data.data(), 1, img.size(), fp) == img.size();
+    fclose(fp);
+    return ok;
+}
+
+// save_one_image_rgb() of split_image_blur.c:40-56, as PPM.
+inline bool save_ppm(const char *path, const unsigned char *interleaved, int width, int height)
+{
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return false;
+    fprintf(fp, "P6\n%d %d\n255\n", width, height);
+    const size_t n = (size_t)width * height * 3;
+    const bool ok = fwrite(interleaved, 1, n, fp) == n;
+    fclose(fp);
+    return ok;
+}
+
+// Seeded synthetic photo-like image (smooth gradients + texture) for when no input file is given.
+inline void make_synthetic(Image &img, int width, int height, uint64_t seed)
+{
+    img.width = width; img.height = height; img.channels = 3;
+    img.data.resize(img.size());
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 1;
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            const int noise = (int)((s >> 33) & 63);
+            unsigned char *p = &img.data[((size_t)y * width + x) * 3];
+            p[0] = (unsigned char)((x * 255 / (width > 1 ? width - 1 : 1) + noise) & 255);
+            p[1] = (unsigned char)((y * 255 / (height > 1 ? height - 1 : 1) + noise) & 255);
+            p[2] = (unsigned char)(((x ^ y) * 3 + noise) & 255);
+        }
+}
+
+// 64-bit FNV-1a over a byte range: lets a run print a checksum of everything it produced.
+inline uint64_t fnv1a(const unsigned char *p, size_t n, uint64_t h = 1469598103934665603ull)
+{
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+// Options that follow the reference's positional arguments.  The positional surface is unchanged; these only expose
+// what the reference hard-codes (heterogeneous_blur.c:43-48) so BASELINE.json's other shapes can be run.
+struct ExtraOptions {
+    std::string input;        // --input file.ppm          (default ./image_320x240.ppm, else synthetic)
+    int width = 320, height = 240;  // --width/--height     (synthetic source only)
+    int num_images = 5000;    // --images N                (NUM_IMAGES)
+    int gpus = 0;             // --gpus G                  (0 = all visible)
+    bool resident = false;    // --resident                (keep the stream in HBM: kernels only, no host copies)
+    bool quiet = false;       // --quiet                   (no per-batch progress lines)
+    std::string save;         // --save out.ppm            (write output image 0)
+    bool checksum = false;    // --checksum                (FNV-1a of all outputs, end-to-end mode)
+    int repeat = 1;           // --repeat R                (resident mode: passes over the stream)
+    bool host_halo = false;   // --host-halo               (Approach 2: upload halo rows from the host like the reference)
+};
+
+inline int parse_extra(int argc, char **argv, int first, ExtraOptions &o)
+{
+    for (int i = first; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&](const char *name) -> const char * {
+            if (i + 1 >= argc) { printf("Error: %s needs a value\n", name); exit(-1); }
+            return argv[++i];
+        };
+        if (a == "--input") o.input = val("--input");
+        else if (a == "--width") o.width = atoi(val("--width"));
+        else if (a == "--height") o.height = atoi(val("--height"));
+        else if (a == "--images") o.num_images = atoi(val("--images"));
+        else if (a == "--gpus") o.gpus = atoi(val("--gpus"));
+        else if (a == "--resident") o.resident = true;
+        else if (a == "--quiet") o.quiet = true;
+        else if (a == "--save") o.save = val("--save");
+        else if (a == "--checksum") o.checksum = true;
+        else if (a == "--repeat") o.repeat = atoi(val("--repeat"));
+        else if (a == "--host-halo") o.host_halo = true;
+        else { printf("Error: unknown option %s\n", a.c_str()); return -1; }
+    }
+    if (o.width < 1 || o.height < 1 || o.num_images < 1 || o.repeat < 1) { printf("Error: bad size option\n"); return -1; }
+    return 0;
+}
+
+// The reference's LOAD ORIGINAL IMAGE section (heterogeneous_blur.c:104-137) without CImg/libjpeg.
+inline void load_source_image(const ExtraOptions &o, Image &img, std::string &name)
+{
+    if (!o.input.empty()) {
+        if (!load_ppm(o.input.c_str(), img)) { printf("Error: cannot read PPM file %s\n", o.input.c_str()); exit(-1); }
+        name = o.input;
+    } else if (o.width == 320 && o.height == 240 && load_ppm("./image_320x240.ppm", img)) {
+        name = "./image_320x240.ppm";
+    } else {
+        make_synthetic(img, o.width, o.height, 2026);
+        name = "(synthetic " + std::to_string(o.width) + "x" + std::to_string(o.height) + ")";
+    }
+}
+
+struct DeviceTimes {
+    double in_ms = 0, kernel_ms = 0, out_ms = 0;
+    long long images = 0;
+    double total() const { return in_ms + kernel_ms + out_ms; }
+};

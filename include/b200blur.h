@@ -92,6 +92,9 @@ B200BLUR_API int b200blur_enqueue_marker(b200blur_ctx *ctx, int queue, b200blur_
 B200BLUR_API int b200blur_events_elapsed_ms(b200blur_ctx *ctx, b200blur_event from, b200blur_event to, double *ms);
 /* Make `queue` wait for the END of `ev` (cross-queue dependency; OpenCL's event wait list). */
 B200BLUR_API int b200blur_enqueue_wait(b200blur_ctx *ctx, int queue, b200blur_event ev);
+/* Same, for an event that belongs to ANOTHER context (another GPU): orders a band's kernel after its neighbours'
+ * uploads when halo rows are read from peer memory.  The event must already have been enqueued by its owner. */
+B200BLUR_API int b200blur_enqueue_wait_peer(b200blur_ctx *ctx, int queue, b200blur_ctx *src, b200blur_event ev);
 
 /* ----------------------------------------------------------------------------------------------- transfers
  * Asynchronous, in order on `queue`.  Host memory should be pinned (host_alloc/host_register); the caller keeps

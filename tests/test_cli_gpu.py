@@ -1,0 +1,82 @@
+"""GPU tests of the two drop-in CLIs (C++ host programs over the C ABI): their saved output image must equal the oracle's
+blur of the input they were given, for Approach 1 and Approach 2, end-to-end and device-resident."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "heterogeneous-opencl-image-processing-engine_b200", "bin")
+
+
+def write_ppm(path, img):
+    h, w, _ = img.shape
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        f.write(img.tobytes())
+
+
+def read_ppm(path):
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"P6"
+        w, h = map(int, f.readline().split())
+        assert f.readline().strip() == b"255"
+        return np.frombuffer(f.read(), np.uint8).reshape(h, w, 3)
+
+
+def n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.fixture(scope="module")
+def photo(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    img = np.random.default_rng(5).integers(0, 256, size=(240, 320, 3), dtype=np.uint8)
+    path = os.path.join(d, "in.ppm")
+    write_ppm(path, img)
+    return d, path, img, oracle.c_blur(img)
+
+
+def run(cmd, cwd):
+    out = subprocess.run(cmd, cwd=cwd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    return out.stdout
+
+
+@pytest.mark.parametrize("extra", [[], ["--resident"]], ids=["end-to-end", "resident"])
+@pytest.mark.parametrize("mode", ["gpu", "both", "cpu"])
+def test_heterogeneous_blur_cli(photo, mode, extra):
+    d, path, img, want = photo
+    out_path = os.path.join(d, f"a1_{mode}_{len(extra)}.ppm")
+    text = run([os.path.join(BIN, "heterogeneous_blur"), mode, "0.728", "35", "--images", "143", "--input", path,
+                "--save", out_path, "--quiet", "--checksum"] + extra, d)
+    assert "HETEROGENEOUS CONFIGURATION" in text and "7. THROUGHPUT" in text and "Images per second" in text
+    assert "Number of batches: 5" in text  # ceil(143/35), heterogeneous_blur.c:86
+    assert np.array_equal(read_ppm(out_path), want)
+
+
+def test_heterogeneous_blur_cli_argument_handling(photo):
+    d, path, _, _ = photo
+    text = run([os.path.join(BIN, "heterogeneous_blur"), "nonsense", "7", "99999", "--images", "10", "--input", path, "--quiet"], d)
+    # heterogeneous_blur.c:62-65, :72-75, :80-83
+    assert "Usage:" in text and "Defaulting to heterogeneous mode." in text
+    assert "Warning: gpu_ratio must be between 0.0 and 1.0. Using 0.5" in text
+    assert "Warning: BATCH_SIZE must be between 1 and 10. Using 500" in text
+
+
+@pytest.mark.parametrize("extra", [[], ["--resident"], ["--host-halo"]], ids=["p2p", "resident", "host-halo"])
+def test_split_image_blur_cli(photo, extra):
+    d, path, img, want = photo
+    g = min(n_gpus(), 8)
+    out_path = os.path.join(d, f"a2_{len(extra)}_{'_'.join(extra)}.ppm")
+    text = run([os.path.join(BIN, "split_image_blur"), "0.837", "35", "--images", "80", "--input", path, "--save", out_path,
+                "--quiet", "--checksum"] + extra, d)
+    assert "SPLIT-IMAGE CONFIGURATION" in text and "split row 39" in text  # split_image_blur.c:144 known answer
+    assert f"Row bands over {g} GPU(s)" in text and "9. OPTIMAL RATIO RECOMMENDATION" in text
+    assert np.array_equal(read_ppm(out_path), want)
