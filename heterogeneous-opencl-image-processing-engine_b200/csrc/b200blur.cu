@@ -74,6 +74,9 @@ struct b200blur_ctx {
     size_t ring_slot_bytes = 0;
     // work counters of the streamed kernel: two 64-bit words per queue, zero between launches
     unsigned long long *d_work = nullptr;
+    // per-kernel launch facts (max dynamic smem attribute set, resident CTAs/SM), cached: both calls are slow
+    struct KernelInfo { const void *fn; int block; size_t smem; int per_sm; };
+    std::vector<KernelInfo> kernel_info;
 };
 
 namespace {
@@ -254,10 +257,15 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
     if (smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", smem);
     StreamKernel fn = cfg.fn[p.channels - 1];
     if (ctx->v2_debug == 1 && p.channels == 3 && cfg.rb == 8 && cfg.ns == 4) fn = b200blur::blur_stream_kernel<3, 8, 4, 1>;
-    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
-    if (per_sm < 1) return fail(B200BLUR_ERR_CUDA, "streamed kernel does not fit on an SM");
+    for (auto &ki : ctx->kernel_info)
+        if (ki.fn == (const void *)fn && ki.block == block && ki.smem == smem) per_sm = ki.per_sm;
+    if (per_sm == 0) {
+        CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
+        if (per_sm < 1) return fail(B200BLUR_ERR_CUDA, "streamed kernel does not fit on an SM");
+        ctx->kernel_info.push_back({(const void *)fn, block, smem, per_sm});
+    }
     if (ctx->v2_ctas_per_sm > 0 && per_sm > ctx->v2_ctas_per_sm) per_sm = ctx->v2_ctas_per_sm;
     const long long slots = (long long)ctx->sm_count * per_sm;
     sp.img_blocks = (p.n_images + sp.ipc - 1) / sp.ipc;
