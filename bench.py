@@ -328,7 +328,7 @@ def run_b200_arm(args) -> None:
                     "d2h_bytes_per_step": N_IMAGES * IMAGE_BYTES, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "host_link_GBps_each_way": N_IMAGES * IMAGE_BYTES * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                     "stage_ms_last_step": {"h2d": last.h2d_ms, "kernel": last.kernel_ms, "d2h": last.d2h_ms},
-                    "api": "b200blur_run_host (pinned host buffers, 3 queues, 4-slot device ring)"},
+                    "api": "b200blur_run_host (pinned host buffers, 3 queues, 4-slot device ring, batches fused into ~64 MB transfer chunks)"},
             "gpu_launches": int(resident_launches + e2e_launches),
             "clocks": clocks,
             "published_reference_context": {"a1_best_images_per_s": 8568, "hardware": "i7-12700 + UHD 770",

@@ -261,7 +261,8 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
     for (auto &ki : ctx->kernel_info)
         if (ki.fn == (const void *)fn && ki.block == block && ki.smem == smem) per_sm = ki.per_sm;
     if (per_sm == 0) {
-        CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // opt in to the largest dynamic shared-memory size once per kernel (any later, smaller request is covered)
+        CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
         if (per_sm < 1) return fail(B200BLUR_ERR_CUDA, "streamed kernel does not fit on an SM");
         ctx->kernel_info.push_back({(const void *)fn, block, smem, per_sm});
@@ -827,7 +828,32 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
     const size_t image_bytes = (size_t)width * height * channels;
     if (n_images && image_bytes && (!h_in || !h_out)) return fail(B200BLUR_ERR_INVALID, "host pointer is NULL");
     CU_TRY(cudaSetDevice(ctx->device));
-    const int n_slots = 4;
+    // Transfer granularity.  Batches are independent, so the pipeline moves and launches them in chunks of about
+    // 64 MB: several small batches fused, or a large batch cut into pieces.  (At one 8 MB batch per transfer the
+    // per-chunk event/dependency gaps cap the link at 33 GB/s each way; at 64 MB it reaches the 45 GB/s this host link
+    // sustains with both directions active -- tools/linkbench.py, tools/e2e.py.)  B200BLUR_E2E_CHUNK_MB overrides the
+    // target (0 = exactly one batch per chunk, the reference's granularity); B200BLUR_RING overrides the ring depth.
+    static const int env_ring = getenv("B200BLUR_RING") ? atoi(getenv("B200BLUR_RING")) : 0;
+    static const int env_chunk_mb = getenv("B200BLUR_E2E_CHUNK_MB") ? atoi(getenv("B200BLUR_E2E_CHUNK_MB")) : 64;
+    const int n_slots = env_ring > 1 ? env_ring : 4;
+    if (env_chunk_mb > 0 && image_bytes > 0) {
+        const double target = (double)env_chunk_mb * 1024 * 1024;
+        const double batch_bytes = (double)batch_size * image_bytes;
+        long long chunk = batch_size;
+        if (batch_bytes < target) {
+            long long fuse = (long long)(target / batch_bytes + 0.5);
+            const long long n_batches = (n_images + batch_size - 1) / batch_size;
+            if (fuse > n_batches / 8) fuse = n_batches / 8;   // keep at least ~8 chunks in the pipeline
+            if (fuse < 1) fuse = 1;
+            chunk = (long long)batch_size * fuse;
+        } else if (batch_bytes > 2 * target) {
+            long long pieces = (long long)(batch_bytes / target + 0.5);
+            chunk = (batch_size + pieces - 1) / pieces;
+            if (chunk < 1) chunk = 1;
+        }
+        if (chunk > 0x7fffffffLL) chunk = 0x7fffffffLL;
+        batch_size = (int)chunk;
+    }
     if (int rc = ring_prepare(ctx, image_bytes * (size_t)batch_size, n_slots)) return rc;
     cudaStream_t q_in = ctx->queues[0], q_k = ctx->queues[1], q_out = ctx->queues[2];
     const double t0 = now_ms();

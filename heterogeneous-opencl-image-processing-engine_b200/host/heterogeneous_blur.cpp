@@ -189,7 +189,7 @@ int main(int argc, char **argv)
             void *d_in, *d_out, *h;
             blur_check(b200blur_dev_alloc(w.ctx, count * image_size, &d_in), "Failed to create input buffer");
             blur_check(b200blur_dev_alloc(w.ctx, count * image_size, &d_out), "Failed to create output buffer");
-            const int64_t stage = std::min<int64_t>(count, 256);
+            const int64_t stage = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(count, 256), (256ll << 20) / (int64_t)image_size));
             blur_check(b200blur_host_alloc(stage * image_size, &h), "Failed to allocate pinned staging");
             for (int64_t i = 0; i < stage; i++) memcpy((unsigned char *)h + i * image_size, original_image, image_size);
             for (int64_t i = 0; i < count; i += stage) {

@@ -248,8 +248,9 @@ int main(int argc, char **argv)
         if (opt.resident) {
             // bands of all images resident in HBM; halo rows read from the neighbours' resident buffers
             void *h;
-            const long long stage = std::min<long long>(NUM_IMAGES, 256);
             const size_t band_bytes = (size_t)w.in_rows * pitch;
+            // staging buffer of at most ~256 MB (large frames: a few images at a time)
+            const long long stage = std::max<long long>(1, std::min<long long>(std::min<long long>(NUM_IMAGES, 256), (256ll << 20) / (long long)band_bytes));
             blur_check(b200blur_host_alloc(stage * band_bytes, &h), "Failed to allocate pinned staging");
             fill_rows(w, (unsigned char *)h, stage);
             for (long long i = 0; i < NUM_IMAGES; i += stage) {

@@ -200,7 +200,9 @@ B200BLUR_API int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void
                                        b200blur_stats *stats);
 /* End to end: `h_in`/`h_out` are HOST buffers (pinned for full speed) of n_images tight images.  Chunks of
  * `batch_size` images flow H2D -> blur -> D2H through a ring of device buffers on separate queues so the three
- * stages of different chunks overlap (the reference serialises them per image). */
+ * stages of different chunks overlap (the reference serialises them per image).  Batches are
+ * independent, so small batches are fused (and very large ones cut) into ~64 MB transfer chunks; stats->launches
+ * reports the kernels actually launched. */
 B200BLUR_API int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int width, int height,
                                    int channels, int64_t n_images, int batch_size, b200blur_stats *stats);
 
