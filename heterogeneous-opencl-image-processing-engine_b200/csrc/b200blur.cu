@@ -271,23 +271,19 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
     const long long slots = (long long)ctx->sm_count * per_sm;
     sp.img_blocks = (p.n_images + sp.ipc - 1) / sp.ipc;
     // Work unit = `seg` output rows of `ipc` images (or of one column block): ~48 KB in + 48 KB out for full-width
-    // rows, ~128 KB for column blocks, and seg + 2 input rows fill whole slots ((seg + 2) % RB == 0).
+    // rows, ~128 KB for column blocks; the band is cut into equal segments of about that size.
     int seg;
     if (ctx->v2_seg > 0) {
         seg = ctx->v2_seg;
     } else {
         const double unit_bytes = sp.ncb == 1 ? 48.0 * 1024 : 128.0 * 1024;
         const double row_bytes = (double)sp.ipc * sp.cb * 16;
-        int m = (int)((unit_bytes / row_bytes + 2.0) / cfg.rb + 0.5);
-        if (m < 1) m = 1;
-        seg = m * cfg.rb - 2;
+        long long want = (long long)(unit_bytes / row_bytes + 0.5);
+        if (want < 6) want = 6;
         // few images: shorter units so that every SM gets several
-        while (seg > cfg.rb - 2 && sp.img_blocks * sp.ncb * ((p.rows + seg - 1) / seg) < 2 * slots) {
-            m = (m + 1) / 2;
-            seg = m * cfg.rb - 2;
-            if (m == 1) break;
-        }
-        if (seg < 2) seg = 2;
+        while (want > 6 && sp.img_blocks * sp.ncb * ((p.rows + want - 1) / want) < 2 * slots) want = (want + 1) / 2;
+        const long long nseg = (p.rows + want - 1) / want;
+        seg = (int)((p.rows + nseg - 1) / nseg);
     }
     if (seg > p.rows) seg = p.rows;
     sp.seg = seg;

@@ -449,6 +449,7 @@ blur_stream_kernel(const StreamParams sp)
             uint32_t a = ring + (uint32_t)(buf * sp.slot_bytes) + lane_off;
 #pragma unroll
             for (int r = 0; r < RB; r++) {
+                if (k >= k_end) break;                  // short last slot of an item (uniform across the CTA)
                 const uint4 w = ptx::lds128(a);
                 uint32_t wl = ptx::lds32(a - 4);
                 uint32_t wr = ptx::lds32(a + 16);
@@ -470,7 +471,7 @@ blur_stream_kernel(const StreamParams sp)
                 o.z = __byte_perm(v[4], v[5], 0x7351);
                 o.w = __byte_perm(v[6], v[7], 0x7351);
                 if (DBG == 1) o = w;
-                if (active && k >= 2 && k < k_end) stg128_stream(dst, o);
+                if (active && k >= 2) stg128_stream(dst, o);
                 dst += sp.b.pitch;
                 k++;
             }

@@ -209,6 +209,29 @@ def test_separate_band_buffers_with_explicit_halo_rows(ctx):
     assert_same(out, want[:, r0:r1])
 
 
+@pytest.mark.parametrize("shape", [(5, 40, 320, 3), (3, 17, 2048, 3), (4, 9, 16, 3), (3, 7, 21, 3), (2, 1, 256, 3), (3, 2, 128, 3)])
+def test_no_writes_outside_the_output_range(ctx, shape):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds stores are caught with guard bands: the output
+    sits between two 64 KB canaries that must come back untouched (the streamed kernel's store pointer deliberately
+    starts two rows before the output and relies on predication)."""
+    n, h, w, c = shape
+    x = synth(sum(shape), n, h, w, c)
+    guard = 65536
+    total = guard + x.nbytes + guard
+    host = np.full(total, 0xAB, np.uint8)
+    d_in, d_buf = ctx.dev_alloc(x.nbytes), ctx.dev_alloc(total)
+    ctx.enqueue_write(0, d_in, x, x.nbytes)
+    ctx.enqueue_write(0, d_buf, host, total)
+    ctx.enqueue_blur(0, ctx.launch_rows(d_in, d_buf + guard, w, h, c, 0, h, n))
+    back = np.zeros(total, np.uint8)
+    ctx.enqueue_read(0, back, d_buf, total)
+    ctx.finish()
+    ctx.dev_free(d_in)
+    ctx.dev_free(d_buf)
+    assert (back[:guard] == 0xAB).all() and (back[guard + x.nbytes:] == 0xAB).all()
+    assert_same(back[guard:guard + x.nbytes].reshape(shape), oracle.c_blur_batch(x))
+
+
 def test_image_strides_larger_than_image(ctx):
     n, h, w, c = 3, 12, 32, 3
     img_bytes = h * w * c
