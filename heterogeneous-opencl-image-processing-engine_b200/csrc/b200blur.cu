@@ -77,6 +77,8 @@ struct b200blur_ctx {
     // per-kernel launch facts (max dynamic smem attribute set, resident CTAs/SM), cached: both calls are slow
     struct KernelInfo { const void *fn; int block; size_t smem; int per_sm; };
     std::vector<KernelInfo> kernel_info;
+    cudaEvent_t fork_event = nullptr;          // fork/join of the per-batch launches of b200blur_run_resident
+    std::vector<cudaEvent_t> join_events;
 };
 
 namespace {
@@ -449,6 +451,9 @@ int b200blur_ctx_destroy(b200blur_ctx *ctx)
     for (auto q : ctx->queues) cudaStreamSynchronize(q);
     ring_release(ctx);
     if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+    for (auto e : ctx->join_events)
+        if (e) cudaEventDestroy(e);
     for (auto &e : ctx->events) {
         if (e.start) cudaEventDestroy(e.start);
         if (e.end) cudaEventDestroy(e.end);
@@ -774,7 +779,24 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
         if (int rc = event_begin(ctx, 0, &ev_all, &slot)) return rc;
     int64_t launches = 0;
     const int64_t step = coalesce ? (n_images > 0 ? n_images : 1) : batch_size;
-    for (int64_t i0 = 0; i0 < n_images; i0 += step) {
+    // One launch per batch (coalesce == 0): the batches are independent, so their launches are spread round-robin
+    // over all queues of the context and overlap each other's ramp-up and tail; queue 0 forks and joins the others,
+    // so the call still behaves like one in-order operation on queue 0.
+    const int nq = (!coalesce && n_images > (int64_t)batch_size) ? (int)ctx->queues.size() : 1;
+    cudaEvent_t fork = nullptr;
+    if (nq > 1) {
+        if (!ctx->fork_event) CU_TRY(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+        if (ctx->join_events.size() < ctx->queues.size()) {
+            ctx->join_events.resize(ctx->queues.size(), nullptr);
+            for (auto &e : ctx->join_events)
+                if (!e) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        fork = ctx->fork_event;
+        CU_TRY(cudaEventRecord(fork, s));
+        for (int q = 1; q < nq; q++) CU_TRY(cudaStreamWaitEvent(ctx->queues[q], fork, 0));
+    }
+    int64_t bi = 0;
+    for (int64_t i0 = 0; i0 < n_images; i0 += step, bi++) {
         const int64_t n = (n_images - i0 < step) ? n_images - i0 : step;
         b200blur_launch l;
         if (int rc = b200blur_launch_rows(&l, static_cast<const uint8_t *>(d_in) + (size_t)i0 * image_bytes,
@@ -783,8 +805,12 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
             return rc;
         if (int rc = launch_validate(&l)) return rc;
         int nk;
-        if (int rc = do_launch(ctx, 0, &l, &nk)) return rc;
+        if (int rc = do_launch(ctx, (int)(bi % nq), &l, &nk)) return rc;
         launches += nk;
+    }
+    for (int q = 1; q < nq; q++) {
+        CU_TRY(cudaEventRecord(ctx->join_events[q], ctx->queues[q]));
+        CU_TRY(cudaStreamWaitEvent(s, ctx->join_events[q], 0));
     }
     if (stats) {
         if (int rc = event_end(ctx, 0, slot)) return rc;
