@@ -115,6 +115,7 @@ struct ExtraOptions {
     bool checksum = false;    // --checksum                (FNV-1a of all outputs, end-to-end mode)
     int repeat = 1;           // --repeat R                (resident mode: passes over the stream)
     bool host_halo = false;   // --host-halo               (Approach 2: upload halo rows from the host like the reference)
+    int fill_threads = 4;     // --fill-threads T          (host threads per GPU that replicate the source image into staging)
 };
 
 inline int parse_extra(int argc, char **argv, int first, ExtraOptions &o)
@@ -136,6 +137,7 @@ inline int parse_extra(int argc, char **argv, int first, ExtraOptions &o)
         else if (a == "--checksum") o.checksum = true;
         else if (a == "--repeat") o.repeat = atoi(val("--repeat"));
         else if (a == "--host-halo") o.host_halo = true;
+        else if (a == "--fill-threads") o.fill_threads = atoi(val("--fill-threads"));
         else { printf("Error: unknown option %s\n", a.c_str()); return -1; }
     }
     if (o.width < 1 || o.height < 1 || o.num_images < 1 || o.repeat < 1) { printf("Error: bad size option\n"); return -1; }
@@ -156,8 +158,26 @@ inline void load_source_image(const ExtraOptions &o, Image &img, std::string &na
     }
 }
 
+// The reference's "copy original image to each slot" loop (heterogeneous_blur.c:440-442), spread over a few host
+// threads: one core replicates at ~20 GB/s, the host link moves ~45-55 GB/s, so a single thread would be the bottleneck.
+#include <thread>
+inline void replicate_rows(unsigned char *dst, const unsigned char *src, size_t bytes_each, long long count, int threads)
+{
+    if (threads < 1) threads = 1;
+    if (count < 2 * threads || (double)count * bytes_each < 8e6) threads = 1;
+    auto work = [&](long long a, long long b) {
+        for (long long i = a; i < b; i++) memcpy(dst + (size_t)i * bytes_each, src, bytes_each);
+    };
+    if (threads == 1) { work(0, count); return; }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work, count * t / threads, count * (t + 1) / threads);
+    work(0, count / threads);
+    for (auto &t : pool) t.join();
+}
+
 struct DeviceTimes {
     double in_ms = 0, kernel_ms = 0, out_ms = 0;
+    double fill_ms = 0;  // host time spent replicating the source image into staging (inside the wall-clock window)
     long long images = 0;
     double total() const { return in_ms + kernel_ms + out_ms; }
 };

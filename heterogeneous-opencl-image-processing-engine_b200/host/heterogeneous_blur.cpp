@@ -140,6 +140,11 @@ int main(int argc, char **argv)
         b200blur_partition(BATCH_SIZE, G, k, &b, &c);
         max_share = std::max<long long>(max_share, c);
     }
+    // Batches are independent, so a GPU's shares of `fuse` consecutive batches travel and launch together: ~64 MB per
+    // transfer keeps the host link at its ceiling (8 MB transfers reach only ~33 of 45 GB/s, tools/e2e.py).
+    long long fuse = (long long)((64.0 * 1024 * 1024) / ((double)max_share * image_size) + 0.5);
+    fuse = std::max(1LL, std::min<long long>(fuse, std::max(1, NUM_BATCHES / 8)));
+    const long long slot_images = max_share * fuse;
     for (int k = 0; k < G; k++) {
         Worker &w = workers[k];
         w.gpu = k;
@@ -147,16 +152,16 @@ int main(int argc, char **argv)
         if (!opt.resident) {
             w.ring.resize(kRing);
             for (auto &s : w.ring) {
-                blur_check(b200blur_host_alloc(max_share * image_size, (void **)&s.h_in), "Failed to allocate pinned input");
-                blur_check(b200blur_host_alloc(max_share * image_size, (void **)&s.h_out), "Failed to allocate pinned output");
-                blur_check(b200blur_dev_alloc(w.ctx, max_share * image_size, &s.d_in), "Failed to create input buffer");
-                blur_check(b200blur_dev_alloc(w.ctx, max_share * image_size, &s.d_out), "Failed to create output buffer");
+                blur_check(b200blur_host_alloc(slot_images * image_size, (void **)&s.h_in), "Failed to allocate pinned input");
+                blur_check(b200blur_host_alloc(slot_images * image_size, (void **)&s.h_out), "Failed to allocate pinned output");
+                blur_check(b200blur_dev_alloc(w.ctx, slot_images * image_size, &s.d_in), "Failed to create input buffer");
+                blur_check(b200blur_dev_alloc(w.ctx, slot_images * image_size, &s.d_out), "Failed to create output buffer");
             }
         }
     }
     printf("Device buffers allocated\n\n");
-    printf("Global work size: %d x %d per image, %lld image(s) per launch\n", (width + 15) / 16 * 16, (height + 15) / 16 * 16,
-           max_share);
+    printf("Global work size: %d x %d per image, up to %lld image(s) per launch (%lld batch share(s) fused)\n",
+           (width + 15) / 16 * 16, (height + 15) / 16 * 16, slot_images, fuse);
     printf("Local work size: 16 x 16 (reference geometry; the CUDA kernel tiles 16-byte columns x row strips)\n\n");
 
     printf("Starting batch processing of %d images in %d batches...\n\n", NUM_IMAGES, NUM_BATCHES);
@@ -220,29 +225,37 @@ int main(int argc, char **argv)
             return;
         }
         long long issued = 0;
-        for (int batch = 0; batch < NUM_BATCHES; batch++) {
-            const int batch_start = batch * BATCH_SIZE;
-            int batch_count = BATCH_SIZE;
-            if (batch_start + batch_count > NUM_IMAGES) batch_count = NUM_IMAGES - batch_start;  // :423-427
-            if (k == 0 && !opt.quiet) {
-                printf("=== Processing Batch %d/%d ===\n", batch + 1, NUM_BATCHES);
-                printf("  Batch work distribution:");
-                for (int j = 0; j < G; j++) {
-                    int64_t b, c;
-                    b200blur_partition(batch_count, G, j, &b, &c);
-                    printf(" GPU%d=%lld", j, (long long)c);
+        for (int batch0 = 0; batch0 < NUM_BATCHES; batch0 += (int)fuse) {
+            // this GPU's shares of batches [batch0, batch0 + fuse)
+            long long count = 0, first_image = -1;
+            for (int batch = batch0; batch < std::min<long long>(NUM_BATCHES, batch0 + fuse); batch++) {
+                const int batch_start = batch * BATCH_SIZE;
+                int batch_count = BATCH_SIZE;
+                if (batch_start + batch_count > NUM_IMAGES) batch_count = NUM_IMAGES - batch_start;  // :423-427
+                if (k == 0 && !opt.quiet) {
+                    printf("=== Processing Batch %d/%d ===\n", batch + 1, NUM_BATCHES);
+                    printf("  Batch work distribution:");
+                    for (int j = 0; j < G; j++) {
+                        int64_t b, c;
+                        b200blur_partition(batch_count, G, j, &b, &c);
+                        printf(" GPU%d=%lld", j, (long long)c);
+                    }
+                    printf("\n");
                 }
-                printf("\n");
+                int64_t begin, c;
+                b200blur_partition(batch_count, G, k, &begin, &c);  // replaces (int)(batch_count * gpu_ratio), :449-451
+                if (c > 0 && first_image < 0) first_image = batch_start + begin;
+                count += c;
             }
-            int64_t begin, count;
-            b200blur_partition(batch_count, G, k, &begin, &count);  // replaces (int)(batch_count * gpu_ratio), :449-451
             if (count == 0) continue;
             Slot &s = w.ring[issued % kRing];
             if (s.busy) harvest(w, s);
             s.count = count;
-            s.first_image = batch_start + begin;
+            s.first_image = first_image;
             // CREATE BATCH IMAGE STREAM (:431-442): replicate the source image into this share's staging slots
-            for (int64_t i = 0; i < count; i++) memcpy(s.h_in + i * image_size, original_image, image_size);
+            const double tf = get_time_ms();
+            replicate_rows(s.h_in, original_image, image_size, count, opt.fill_threads);
+            w.t.fill_ms += get_time_ms() - tf;
             const size_t bytes = (size_t)count * image_size;
             blur_check(b200blur_enqueue_write(w.ctx, 0, s.d_in, s.h_in, bytes, &s.ev_in), "GPU write failed");
             blur_check(b200blur_enqueue_wait(w.ctx, 1, s.ev_in), "GPU wait failed");
@@ -294,7 +307,9 @@ int main(int argc, char **argv)
         printf("   - Transfer IN:         %.2f ms (%.1f%%)\n", t.in_ms, tot > 0 ? t.in_ms / tot * 100 : 0.0);
         printf("   - Kernel execution:    %.2f ms (%.1f%%)\n", t.kernel_ms, tot > 0 ? t.kernel_ms / tot * 100 : 0.0);
         printf("   - Transfer OUT:        %.2f ms (%.1f%%)\n", t.out_ms, tot > 0 ? t.out_ms / tot * 100 : 0.0);
-        printf("   Average per image:     %.5f ms\n\n", tot / t.images);
+        printf("   Average per image:     %.5f ms\n", tot / t.images);
+        if (!opt.resident) printf("   Host staging (replicate source image, %d thread(s)): %.2f ms\n", opt.fill_threads, t.fill_ms);
+        printf("\n");
     }
     printf("====================\n");
 
