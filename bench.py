@@ -185,6 +185,26 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal CPU affinity) BEFORE the pinned staging buffers
+    are allocated, so they are first-touched on the GPU's own NUMA node.  One process per GPU on a two-socket box
+    otherwise lands half the ranks' staging memory on the far socket.  Best effort: returns a note for the JSON."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [i for i in range(n_cpu) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"bound to {len(allowed)} cores near GPU {gpu_index} ({allowed[0]}-{allowed[-1]})"
+        return "NVML affinity empty; not bound"
+    except Exception as e:  # no NVML, container restrictions, ...
+        return f"not bound ({type(e).__name__})"
+
+
 # ----------------------------------------------------------------------------------------------------- product arm
 def run_b200_arm(args) -> None:
     import torch
@@ -201,6 +221,7 @@ def run_b200_arm(args) -> None:
     else:
         torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -334,6 +355,7 @@ def run_b200_arm(args) -> None:
                     "d2h_bytes_per_step": N_IMAGES * IMAGE_BYTES, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "host_link_GBps_each_way": N_IMAGES * IMAGE_BYTES * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                     "stage_ms_last_step": {"h2d": last.h2d_ms, "kernel": last.kernel_ms, "d2h": last.d2h_ms},
+                    "host_affinity": numa,
                     "api": "b200blur_run_host (pinned host buffers, 3 queues, 4-slot device ring, batches fused into ~64 MB transfer chunks)"},
             "gpu_launches": int(resident_launches + e2e_launches),
             "clocks": clocks,
