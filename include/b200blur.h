@@ -194,7 +194,10 @@ typedef struct b200blur_stats {
 
 /* Device-resident: `d_in`/`d_out` hold n_images tight images in HBM.  Images are processed `batch_size` at a
  * time in stream order; when `coalesce` != 0 consecutive batches are fused into as few launches as possible
- * (they are independent), otherwise one launch per batch like the reference's per-batch sync (A1:538). */
+ * (they are independent), otherwise one launch per batch like the reference's per-batch sync (A1:538).  In the
+ * per-batch form the launches are spread over ALL queues of the context (forked from and joined back into queue 0,
+ * so the call still orders like one operation on queue 0) and a repeated identical request is replayed as a CUDA
+ * graph.  stats == NULL makes the call asynchronous (no host synchronisation). */
 B200BLUR_API int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int width, int height,
                                        int channels, int64_t n_images, int batch_size, int coalesce,
                                        b200blur_stats *stats);
