@@ -63,6 +63,7 @@ def parse_args():
 def _cpu_impl():
     """-> (kind, batch_fn, threads): the reference kernel source when oracle/_ref is present, else the oracle port."""
     from oracle import oracle
+    oracle.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
     if oracle.have_ref():
         return "reference", oracle.ref_blur_batch, oracle.ref_num_threads()
     return "port", oracle.c_blur_batch, oracle.num_threads()

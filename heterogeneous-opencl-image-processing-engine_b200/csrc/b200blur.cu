@@ -918,7 +918,7 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
         if (batch_bytes < target) {
             long long fuse = (long long)(target / batch_bytes + 0.5);
             const long long n_batches = (n_images + batch_size - 1) / batch_size;
-            if (fuse > n_batches / 8) fuse = n_batches / 8;   // keep at least ~8 chunks in the pipeline
+            if (fuse > n_batches / 16) fuse = n_batches / 16;   // keep at least ~16 chunks in the pipeline
             if (fuse < 1) fuse = 1;
             chunk = (long long)batch_size * fuse;
         } else if (batch_bytes > 2 * target) {

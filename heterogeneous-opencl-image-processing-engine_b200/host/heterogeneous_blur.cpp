@@ -143,7 +143,7 @@ int main(int argc, char **argv)
     // Batches are independent, so a GPU's shares of `fuse` consecutive batches travel and launch together: ~64 MB per
     // transfer keeps the host link at its ceiling (8 MB transfers reach only ~33 of 45 GB/s, tools/e2e.py).
     long long fuse = (long long)((64.0 * 1024 * 1024) / ((double)max_share * image_size) + 0.5);
-    fuse = std::max(1LL, std::min<long long>(fuse, std::max(1, NUM_BATCHES / 8)));
+    fuse = std::max(1LL, std::min<long long>(fuse, std::max(1, NUM_BATCHES / 16)));  // keep >= 16 pipeline steps per GPU
     const long long slot_images = max_share * fuse;
     for (int k = 0; k < G; k++) {
         Worker &w = workers[k];

@@ -178,7 +178,7 @@ int main(int argc, char **argv)
     long long max_band_rows = 0;
     for (auto &w : workers) max_band_rows = std::max<long long>(max_band_rows, w.in_rows);
     long long fuse = (long long)((64.0 * 1024 * 1024) / ((double)BATCH_SIZE * max_band_rows * pitch) + 0.5);
-    fuse = std::max(1LL, std::min<long long>(fuse, std::max(1, NUM_BATCHES / 8)));
+    fuse = std::max(1LL, std::min<long long>(fuse, std::max(1, NUM_BATCHES / 16)));  // keep >= 16 pipeline steps per GPU
     const long long per_dev_images = opt.resident ? NUM_IMAGES : BATCH_SIZE * fuse;
     for (auto &w : workers) {
         const size_t in_bytes = (size_t)per_dev_images * w.in_rows * pitch, out_bytes = (size_t)per_dev_images * w.rows * pitch;

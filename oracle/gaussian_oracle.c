@@ -128,6 +128,16 @@ ORACLE_API void oracle_blur_batch(const unsigned char *in, unsigned char *out, i
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline must still use all host cores. */
+ORACLE_API void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORACLE_API int oracle_num_threads(void)
 {
 #ifdef _OPENMP

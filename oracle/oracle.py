@@ -148,6 +148,15 @@ def ref_num_threads() -> int:
     return int(_reflib().ref_num_threads())
 
 
+def use_all_cores() -> int:
+    """Make both CPU implementations use every core this process may run on (torchrun sets OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    _lib().oracle_set_num_threads(n)
+    if have_ref():
+        _reflib().ref_set_num_threads(n)
+    return n
+
+
 # ------------------------------------------------------------------------------------------- distribution forms
 def a1_batch_split(batch_count: int, gpu_ratio: float, mode: int = 0):
     """heterogeneous_blur.c:446-458 -> (n_cpu, n_gpu)."""

@@ -64,6 +64,15 @@ REF_API void ref_gaussian_blur_batch(const unsigned char *input, unsigned char *
     }
 }
 
+REF_API void ref_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 REF_API int ref_num_threads(void)
 {
 #ifdef _OPENMP
