@@ -13,7 +13,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -64,7 +63,7 @@ struct b200blur_ctx {
     int kernel_variant = 0;   // 0 auto, 1 register/shuffle strips, 2 TMA-bulk streamed
     int64_t launches = 0;
     // tuning knobs of the streamed kernel (0 = automatic); set from B200BLUR_V2_* at context creation
-    int v2_threads = 0, v2_seg = 0, v2_cfg = 0, v2_ctas_per_sm = 0, v2_debug = 0;
+    int v2_threads = 0, v2_seg = 0, v2_cfg = 0, v2_ctas_per_sm = 0;
     // ring of device buffers owned by b200blur_run_host
     struct Slot {
         uint8_t *d_in = nullptr, *d_out = nullptr;
@@ -268,7 +267,6 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
     const int block = threads + 32;  // + the producer warp
     if (smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", smem);
     StreamKernel fn = cfg.fn[p.channels - 1];
-    if (ctx->v2_debug == 1 && p.channels == 3 && cfg.rb == 8 && cfg.ns == 4) fn = b200blur::blur_stream_kernel<3, 8, 4, 1>;
     int per_sm = 0;
     for (auto &ki : ctx->kernel_info)
         if (ki.fn == (const void *)fn && ki.block == block && ki.smem == smem) per_sm = ki.per_sm;
@@ -421,7 +419,6 @@ int b200blur_ctx_create(int device, int n_queues, b200blur_ctx **out)
     ctx->v2_seg = env_int("B200BLUR_V2_SEG");
     ctx->v2_cfg = env_int("B200BLUR_V2_CFG");
     ctx->v2_ctas_per_sm = env_int("B200BLUR_V2_CTAS");
-    ctx->v2_debug = env_int("B200BLUR_V2_DEBUG");
     for (int i = 0; i < n_queues; i++) {
         cudaStream_t s;
         e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);

@@ -360,7 +360,7 @@ __device__ __forceinline__ void stream_issue_slot(const StreamParams &sp, const 
 // Work is handed out dynamically: the producer takes the next group from a global atomic counter and publishes its
 // index next to the slot (meta[]), so SMs that see more bandwidth simply take more groups.  (A static round-robin
 // persistent grid loses ~10 % of HBM bandwidth on B200 -- tools/membench.cu, profiles/membench_r01.txt.)
-template <int C, int RB, int NS, int DBG = 0>   // DBG = 1 (experiments only): copy the rows instead of blurring them
+template <int C, int RB, int NS>
 __global__ void __launch_bounds__(32 + 256)
 blur_stream_kernel(const StreamParams sp)
 {
@@ -470,7 +470,6 @@ blur_stream_kernel(const StreamParams sp)
                 o.y = __byte_perm(v[2], v[3], 0x7351);
                 o.z = __byte_perm(v[4], v[5], 0x7351);
                 o.w = __byte_perm(v[6], v[7], 0x7351);
-                if (DBG == 1) o = w;
                 if (active && k >= 2) stg128_stream(dst, o);
                 dst += sp.b.pitch;
                 k++;

@@ -34,6 +34,13 @@ def n_gpus():
     return torch.cuda.device_count()
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _binaries():
+    if not (os.path.exists(os.path.join(BIN, "heterogeneous_blur")) and os.path.exists(os.path.join(BIN, "split_image_blur"))):
+        import b200blur
+        b200blur.build()  # nvcc + g++ are part of the image on the GPU box too
+
+
 @pytest.fixture(scope="module")
 def photo(tmp_path_factory):
     d = tmp_path_factory.mktemp("cli")

@@ -88,6 +88,45 @@ def test_generic_path_matches_oracle(ctx, shape):
     assert_same(ctx.blur_numpy(x), oracle.c_blur_batch(x))
 
 
+def test_fuzz_random_shapes_and_row_ranges(ctx):
+    """Seeded fuzz: 80 random (n, h, w, c) -- widths drawn so that the streamed, strip and generic kernels are all hit --
+    each blurred whole and as a random row range of a taller buffer (the b200blur_launch_rows semantics)."""
+    rng = np.random.default_rng(20261018)
+    paths = {True: 0, False: 0}
+    for it in range(80):
+        c = int(rng.choice([1, 2, 3, 3, 3, 4]))
+        kind = it % 4
+        if kind == 0:      # streamed full-width: pitch multiple of 16 and >= 256
+            w = int(rng.integers(6, 120)) * 16 // (1 if c != 3 else 1)
+            w = max(w, 256 // c + 16) // 16 * 16
+        elif kind == 1:    # strips: small pitch multiple of 16
+            w = 16 * int(rng.integers(1, 5)) if c == 3 else 16 * int(rng.integers(1, 4))
+        elif kind == 2:    # column blocks: pitch > 4096
+            w = 16 * int(rng.integers(90, 140))
+        else:              # generic: arbitrary width
+            w = int(rng.integers(1, 200))
+        h = int(rng.integers(1, 70))
+        n = int(rng.integers(1, 5))
+        x = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+        want = oracle.c_blur_batch(x, integer=True)
+        assert_same(ctx.blur_numpy(x), want)
+        paths[ctx.is_vectorised(ctx.launch_rows(0x1000, 0x100000, w, h, c, 0, h, n))] += 1
+        # a row range [r0, r0+nr) of the same buffer, kernel height = h (rows next to the range act as halos)
+        r0 = int(rng.integers(0, h))
+        nr = int(rng.integers(1, h - r0 + 1))
+        P = w * c
+        out = np.zeros((n, nr, w, c), np.uint8)
+        d_in, d_out = ctx.dev_alloc(x.nbytes), ctx.dev_alloc(max(out.nbytes, 16))
+        ctx.enqueue_write(0, d_in, x, x.nbytes)
+        ctx.enqueue_blur(0, ctx.launch_rows(d_in, d_out, w, h, c, r0, nr, n, P * h, P * nr))
+        ctx.enqueue_read(0, out, d_out, out.nbytes)
+        ctx.finish()
+        ctx.dev_free(d_in)
+        ctx.dev_free(d_out)
+        assert_same(out, want[:, r0:r0 + nr])
+    assert paths[True] >= 40 and paths[False] >= 10
+
+
 def test_extreme_values_no_lane_carry(ctx):
     """All-255 and alternating 0/255 inputs drive every packed 16-bit lane to its maximum (4080 << 4)."""
     for h, w in [(20, 64), (240, 320)]:
