@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant override (0 = auto)")
     ap.add_argument("--per-batch", action="store_true", help="resident run launches once per batch (no coalescing)")
+    ap.add_argument("--scheme", choices=["image", "split"], default="image",
+                    help="image = Approach 1 whole-image shards (default, the contract workload); split = Approach 2 row "
+                         "bands of 5000 x 256x256 RGB with halo rows read from the neighbour GPU over NVLink (configs[2])")
     return ap.parse_args()
 
 
@@ -369,10 +372,120 @@ def run_b200_arm(args) -> None:
         dist.destroy_process_group()
 
 
+class _DevView:
+    """Exposes a raw device allocation to torch (as plumbing) through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def run_split_arm(args) -> None:
+    """Approach 2 under one process per GPU (BASELINE.json configs[2]): 5000 x 256x256 RGB, every image cut into
+    WORLD row bands, band k resident on GPU k, halo rows read inside the stencil kernel from the neighbour GPU's memory
+    (CUDA IPC handles exchanged once, NVLink peer loads).  Strong scaling: the stream is fixed, bands shrink with N."""
+    import torch
+    import torch.distributed as dist
+    import b200blur
+    from b200blur.sharding import plan_bands
+
+    n, h, w, c = 5000, 256, 256, 3
+    P = w * c
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = b200blur.Context(local_rank, 4)
+    plans = plan_bands(h, world)
+    me = plans[rank]
+    g = torch.Generator(device=dev).manual_seed(2002)          # same stream on every rank; each keeps only its band
+    stream = torch.randint(0, 256, (n, h, w, c), dtype=torch.uint8, device=dev, generator=g)
+    nbytes = n * me.rows * P
+    d_band, d_out = ctx.dev_alloc(nbytes), ctx.dev_alloc(nbytes)
+    torch.as_tensor(_DevView(d_band, nbytes), device=dev).copy_(stream[:, me.row0:me.row0 + me.rows].reshape(-1))
+    sample_idx = [0, 1, n // 2, n - 1]
+    sample = stream[sample_idx].cpu().numpy() if rank == 0 else None
+    del stream
+    torch.cuda.synchronize()
+    launch = ctx.launch_rows(d_band, d_out, w, me.rows, c, 0, me.rows, n)
+    opened = []
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_export(d_band))
+        if me.has_top:
+            up = plans[rank - 1]
+            base = ctx.ipc_open(handles[rank - 1])
+            opened.append(base)
+            launch.halo_top, launch.halo_top_stride = base + (up.rows - 1) * P, up.rows * P
+        if me.has_bottom:
+            dn = plans[rank + 1]
+            base = ctx.ipc_open(handles[rank + 1])
+            opened.append(base)
+            launch.halo_bottom, launch.halo_bottom_stride = base, dn.rows * P
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        ctx.enqueue_blur(0, launch)
+    ctx.finish(0)
+    barrier()
+    e0 = ctx.enqueue_marker(0)
+    for _ in range(args.steps):
+        ctx.enqueue_blur(0, launch)
+    e1 = ctx.enqueue_marker(0)
+    ctx.finish(0)
+    barrier()
+    ms = ctx.elapsed_ms(e0, e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    parity = None
+    if rank == 0:
+        from oracle import oracle
+        out = torch.as_tensor(_DevView(d_out, nbytes), device=dev).view(n, me.rows, w, c)[sample_idx].cpu().numpy()
+        want = oracle.c_blur_batch(sample, integer=True)[:, me.row0:me.row0 + me.rows]
+        parity = bool((out == want).all())
+        peak = 6650.0
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak = float(json.load(f)["hbm_gbs"])
+        except Exception:
+            pass
+        per_gpu_bytes = 2.0 * n * me.rows * P
+        achieved = per_gpu_bytes / (ms / args.steps * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8 (exact integer arithmetic in packed 16-bit lanes)", "data": "synthetic",
+            "config": {"workload": "A2 split-image: 5000x 256x256 RGB, row bands + 1-row halo over NVLink (BASELINE.json configs[2])",
+                       "bands": [[p.row0, p.rows] for p in plans], "halo": "peer loads inside the stencil kernel (CUDA IPC)",
+                       "parity_vs_oracle_rank0_band": parity},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "blur_stream_kernel<3,8,4>", "per": "GPU (rank 0's band)"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": int(ctx.launch_count)}), flush=True)
+    barrier()
+    for b in opened:
+        ctx.ipc_close(b)
+    ctx.dev_free(d_band)
+    ctx.dev_free(d_out)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main() -> None:
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.scheme == "split":
+        run_split_arm(args)
     else:
         run_b200_arm(args)
 
