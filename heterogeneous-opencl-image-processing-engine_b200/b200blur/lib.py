@@ -26,7 +26,8 @@ class Launch(Structure):
                 ("rows", c_int32), ("reserved", c_int32), ("n_images", c_int64),
                 ("in_image_stride", c_size_t), ("out_image_stride", c_size_t),
                 ("halo_top", c_void_p), ("halo_top_stride", c_size_t),
-                ("halo_bottom", c_void_p), ("halo_bottom_stride", c_size_t)]
+                ("halo_bottom", c_void_p), ("halo_bottom_stride", c_size_t),
+                ("in_row_pitch", c_size_t), ("out_row_pitch", c_size_t)]
 
 
 class Stats(Structure):
@@ -72,6 +73,8 @@ _SIGNATURES = {
     "b200blur_finish_all": (c_int, [c_void_p]),
     "b200blur_launch_rows": (c_int, [POINTER(Launch), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64,
                                      c_size_t, c_size_t]),
+    "b200blur_launch_rows_pitched": (c_int, [POINTER(Launch), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64,
+                                             c_size_t, c_size_t, c_size_t, c_size_t]),
     "b200blur_enqueue_blur": (c_int, [c_void_p, c_int, POINTER(Launch), POINTER(c_int32)]),
     "b200blur_launch_is_vectorised": (c_int, [POINTER(Launch)]),
     "b200blur_set_kernel_variant": (c_int, [c_void_p, c_int]),
@@ -305,15 +308,17 @@ class Context:
     # -- launch construction
     @staticmethod
     def launch_rows(in_ptr, out_ptr, width, in_height, channels, first_row, n_rows, n_images,
-                    in_image_stride=None, out_image_stride=None) -> Launch:
-        """The reference kernel with height=in_height on `in`, keeping rows [first_row, first_row+n_rows)."""
+                    in_image_stride=None, out_image_stride=None, in_row_pitch=0, out_row_pitch=0) -> Launch:
+        """The reference kernel with height=in_height on `in`, keeping rows [first_row, first_row+n_rows).
+        in_row_pitch / out_row_pitch: bytes between rows (0 = tight)."""
         l = Launch()
         if in_image_stride is None:
-            in_image_stride = width * in_height * channels
+            in_image_stride = (in_row_pitch or width * channels) * in_height
         if out_image_stride is None:
-            out_image_stride = width * n_rows * channels
-        _check(load().b200blur_launch_rows(byref(l), _ptr(in_ptr), _ptr(out_ptr), width, in_height, channels, first_row,
-                                           n_rows, n_images, in_image_stride, out_image_stride))
+            out_image_stride = (out_row_pitch or width * channels) * n_rows
+        _check(load().b200blur_launch_rows_pitched(byref(l), _ptr(in_ptr), _ptr(out_ptr), width, in_height, channels,
+                                                   first_row, n_rows, n_images, in_image_stride, out_image_stride,
+                                                   in_row_pitch, out_row_pitch))
         return l
 
     @staticmethod

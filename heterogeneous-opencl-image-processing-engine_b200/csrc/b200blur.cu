@@ -76,6 +76,9 @@ struct b200blur_ctx {
     // per-kernel launch facts (max dynamic smem attribute set, resident CTAs/SM), cached: both calls are slow
     struct KernelInfo { const void *fn; int block; size_t smem; int per_sm; };
     std::vector<KernelInfo> kernel_info;
+    // scratch pair for re-pitching odd-width resident streams (b200blur_run_resident)
+    uint8_t *scratch_in = nullptr, *scratch_out = nullptr;
+    size_t scratch_bytes = 0;
     cudaEvent_t fork_event = nullptr;          // fork/join of the per-batch launches of b200blur_run_resident
     std::vector<cudaEvent_t> join_events;
     // CUDA graph of the last per-batch launch sequence (launch-bound loop: hundreds of small kernels)
@@ -137,11 +140,13 @@ int event_end(b200blur_ctx *ctx, int queue, int slot)
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+size_t in_pitch_of(const b200blur_launch *l) { return l->in_row_pitch ? l->in_row_pitch : (size_t)l->width * l->channels; }
+size_t out_pitch_of(const b200blur_launch *l) { return l->out_row_pitch ? l->out_row_pitch : (size_t)l->width * l->channels; }
+
 bool launch_vectorised(const b200blur_launch *l)
 {
-    const long long pitch = (long long)l->width * l->channels;
     if (l->channels < 1 || l->channels > 4) return false;
-    if (pitch % 16 != 0) return false;
+    if (in_pitch_of(l) % 16 != 0 || out_pitch_of(l) % 16 != 0) return false;
     if (!aligned16(l->in) || !aligned16(l->out)) return false;
     if (l->n_images > 1 && (l->in_image_stride % 16 || l->out_image_stride % 16)) return false;
     if (l->halo_top && (!aligned16(l->halo_top) || (l->n_images > 1 && l->halo_top_stride % 16))) return false;
@@ -157,8 +162,11 @@ int launch_validate(const b200blur_launch *l)
         return fail(B200BLUR_ERR_INVALID, "negative size or channels < 1 (width %d rows %d channels %d n_images %lld)",
                     l->width, l->rows, l->channels, (long long)l->n_images);
     if (l->reserved != 0) return fail(B200BLUR_ERR_INVALID, "launch.reserved must be 0");
-    if ((long long)l->width * l->channels > 0x7fffffffLL)
-        return fail(B200BLUR_ERR_INVALID, "row pitch width*channels exceeds 2^31-1 bytes");
+    const size_t row_bytes = (size_t)l->width * l->channels;
+    if (row_bytes > 0x7fffffffULL || in_pitch_of(l) > 0x7fffffffULL || out_pitch_of(l) > 0x7fffffffULL)
+        return fail(B200BLUR_ERR_INVALID, "row pitch exceeds 2^31-1 bytes");
+    if (in_pitch_of(l) < row_bytes || out_pitch_of(l) < row_bytes)
+        return fail(B200BLUR_ERR_INVALID, "row pitch smaller than width*channels");
     const bool empty = l->width == 0 || l->rows == 0 || l->n_images == 0;
     if (!empty && (!l->in || !l->out)) return fail(B200BLUR_ERR_INVALID, "in/out pointer is NULL");
     if (!empty && l->in == l->out) return fail(B200BLUR_ERR_INVALID, "in-place blur (in == out) is not supported");
@@ -176,7 +184,9 @@ b200blur::BandParams to_params(const b200blur_launch *l)
     p.out_stride = l->out_image_stride;
     p.top_stride = l->halo_top_stride;
     p.bot_stride = l->halo_bottom_stride;
-    p.pitch = l->width * l->channels;
+    p.row_bytes = l->width * l->channels;
+    p.pitch = (int)in_pitch_of(l);
+    p.out_pitch = (int)out_pitch_of(l);
     p.rows = l->rows;
     p.width = l->width;
     p.channels = l->channels;
@@ -187,7 +197,7 @@ b200blur::BandParams to_params(const b200blur_launch *l)
 template <int RS>
 void launch_strip(const b200blur::BandParams &p, cudaStream_t s, long long img0, long long n)
 {
-    const int cpr = p.pitch / 16;
+    const int cpr = p.row_bytes / 16;
     const int n_strips = (p.rows + RS - 1) / RS;
     const long long units = (long long)cpr * n_strips;
     const int block = 256;
@@ -210,15 +220,18 @@ using StreamKernel = void (*)(const b200blur::StreamParams);
 
 struct StreamCfg {
     int rb, ns;
-    StreamKernel fn[4];  // by channels-1
+    StreamKernel fn[4];       // by channels-1: rows end on a chunk boundary
+    StreamKernel fn_edge[4];  // by channels-1: rows end inside a chunk (pitched rows)
 };
 
 template <int RB, int NS>
 constexpr StreamCfg make_cfg()
 {
     return StreamCfg{RB, NS,
-                     {b200blur::blur_stream_kernel<1, RB, NS>, b200blur::blur_stream_kernel<2, RB, NS>,
-                      b200blur::blur_stream_kernel<3, RB, NS>, b200blur::blur_stream_kernel<4, RB, NS>}};
+                     {b200blur::blur_stream_kernel<1, RB, NS, false>, b200blur::blur_stream_kernel<2, RB, NS, false>,
+                      b200blur::blur_stream_kernel<3, RB, NS, false>, b200blur::blur_stream_kernel<4, RB, NS, false>},
+                     {b200blur::blur_stream_kernel<1, RB, NS, true>, b200blur::blur_stream_kernel<2, RB, NS, true>,
+                      b200blur::blur_stream_kernel<3, RB, NS, true>, b200blur::blur_stream_kernel<4, RB, NS, true>}};
 }
 
 // {rows per slot, slots}; index 0 is the default (B200BLUR_V2_CFG selects another for tuning runs)
@@ -227,16 +240,50 @@ const StreamCfg kStreamCfgs[] = {make_cfg<8, 4>(), make_cfg<8, 3>(), make_cfg<4,
 constexpr int kNumStreamCfgs = sizeof(kStreamCfgs) / sizeof(kStreamCfgs[0]);
 
 // Whether the streamed (variant 2) kernel can run this launch: rows wide enough for bulk copies to pay.
-bool stream_eligible(const b200blur::BandParams &p) { return p.pitch >= 256; }
+bool stream_eligible(const b200blur::BandParams &p) { return p.row_bytes >= 256; }
+
+// PRMT selectors that apply the right-edge clamp to the {wl, w, wr} window of the chunk holding the end of a row whose
+// length is not a multiple of 16 (see StreamParams): window byte idx takes the byte C positions earlier when it is one
+// of the C bytes just past the end of the row.  Selector nibbles index the 8 bytes of (previous word, this word).
+void edge_selectors(b200blur::StreamParams &sp, int row_bytes, int channels)
+{
+    const int v = row_bytes - (sp.cpr - 1) * 16;  // bytes of the row inside its last chunk, 1..16
+    sp.edge_general = (v != 16);
+    sp.edge_prev = 0;
+    sp.sel_prev = 0x7654;
+    for (int m = 0; m < 6; m++) sp.sel_last[m] = 0x7654;
+    if (!sp.edge_general) return;
+    const int t0 = v + 4;  // window index of the first byte past the end of the row (window starts 4 bytes before the chunk)
+    for (int m = 1; m < 6; m++) {
+        uint32_t sel = 0;
+        for (int b = 0; b < 4; b++) {
+            const int idx = 4 * m + b;
+            const int src = (idx >= t0 && idx < t0 + channels) ? idx - channels : idx;
+            sel |= (uint32_t)(src - 4 * (m - 1)) << (4 * b);
+        }
+        sp.sel_last[m] = sel;
+    }
+    if (v < 4 && sp.cpr >= 2) {  // the end of the row is within the first word of the last chunk = the wr of the chunk before
+        sp.edge_prev = 1;
+        uint32_t sel = 0;
+        for (int b = 0; b < 4; b++) {
+            const int idx = 20 + b;
+            const int src = (b >= v && b < v + channels) ? idx - channels : idx;
+            sel |= (uint32_t)(src - 16) << (4 * b);
+        }
+        sp.sel_prev = sel;
+    }
+}
 
 int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s, int queue)
 {
     b200blur::StreamParams sp;
     sp.b = p;
-    sp.cpr = p.pitch / 16;
+    sp.cpr = (p.row_bytes + 15) / 16;   // live chunks per row; bytes past row_bytes up to the pitch are padding
+    edge_selectors(sp, p.row_bytes, p.channels);
     const StreamCfg &cfg = kStreamCfgs[(ctx->v2_cfg >= 0 && ctx->v2_cfg < kNumStreamCfgs) ? ctx->v2_cfg : 0];
     int threads;
-    if (sp.cpr <= 256) {
+    if (p.pitch <= 4096) {
         // full-width rows: a CTA step covers `ipc` images side by side; pick the block size that wastes fewest lanes
         sp.cb = sp.cpr;
         sp.ncb = 1;
@@ -261,12 +308,12 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
         sp.margin = 16;
         sp.ipc = 1;
     }
-    sp.sstride = sp.cb * 16 + 2 * sp.margin;
+    sp.sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;   // full-width: rows land exactly as they lie in memory
     sp.slot_bytes = sp.ipc * cfg.rb * sp.sstride;
     const size_t smem = 16 + (size_t)cfg.ns * sp.slot_bytes + 16 + 24 * cfg.ns;
     const int block = threads + 32;  // + the producer warp
     if (smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", smem);
-    StreamKernel fn = cfg.fn[p.channels - 1];
+    StreamKernel fn = sp.edge_general ? cfg.fn_edge[p.channels - 1] : cfg.fn[p.channels - 1];
     int per_sm = 0;
     for (auto &ki : ctx->kernel_info)
         if (ki.fn == (const void *)fn && ki.block == block && ki.smem == smem) per_sm = ki.per_sm;
@@ -317,9 +364,9 @@ int do_launch(b200blur_ctx *ctx, int queue, const b200blur_launch *l, int *n_ker
     if (vec && stream_eligible(p) && ctx->kernel_variant != 1) {
         if (int rc = launch_stream(ctx, p, s, queue)) return rc;
         ++*n_kernels;
-    } else if (vec) {
+    } else if (vec && p.row_bytes % 16 == 0) {
         // strip height: tall strips amortise the two halo rows; short strips expose more threads for small batches
-        const long long cpr = p.pitch / 16;
+        const long long cpr = p.row_bytes / 16;
         const long long threads_rs16 = cpr * ((p.rows + 15) / 16) * p.n_images;
         const bool small = threads_rs16 < (long long)ctx->sm_count * 1024;
         const long long max_grid_y = 65535;
@@ -333,7 +380,7 @@ int do_launch(b200blur_ctx *ctx, int queue, const b200blur_launch *l, int *n_ker
             ++*n_kernels;
         }
     } else {
-        const long long total = (long long)p.rows * p.pitch * p.n_images;
+        const long long total = (long long)p.rows * p.row_bytes * p.n_images;
         long long blocks = (total + 255) / 256;
         const long long cap = (long long)ctx->sm_count * 32;
         if (blocks > cap) blocks = cap;
@@ -459,6 +506,8 @@ int b200blur_ctx_destroy(b200blur_ctx *ctx)
     for (auto q : ctx->queues) cudaStreamSynchronize(q);
     ring_release(ctx);
     if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->scratch_in) cudaFree(ctx->scratch_in);
+    if (ctx->scratch_out) cudaFree(ctx->scratch_out);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     for (auto e : ctx->join_events)
@@ -682,16 +731,19 @@ int b200blur_finish_all(b200blur_ctx *ctx)
 }
 
 // -------------------------------------------------------------------------------------------- kernel launch
-int b200blur_launch_rows(b200blur_launch *l, const void *in, void *out, int width, int in_height, int channels,
-                         int first_row, int n_rows, int64_t n_images, size_t in_image_stride,
-                         size_t out_image_stride)
+int b200blur_launch_rows_pitched(b200blur_launch *l, const void *in, void *out, int width, int in_height, int channels,
+                                 int first_row, int n_rows, int64_t n_images, size_t in_image_stride,
+                                 size_t out_image_stride, size_t in_row_pitch, size_t out_row_pitch)
 {
     if (!l) return fail(B200BLUR_ERR_INVALID, "launch is NULL");
     if (width < 0 || in_height < 0 || channels < 1 || first_row < 0 || n_rows < 0 || n_images < 0 ||
         (long long)first_row + n_rows > in_height)
         return fail(B200BLUR_ERR_INVALID, "bad geometry: width %d in_height %d channels %d rows [%d,%d+%d)", width,
                     in_height, channels, first_row, first_row, n_rows);
-    const size_t pitch = (size_t)width * channels;
+    const size_t row_bytes = (size_t)width * channels;
+    if ((in_row_pitch && in_row_pitch < row_bytes) || (out_row_pitch && out_row_pitch < row_bytes))
+        return fail(B200BLUR_ERR_INVALID, "row pitch smaller than width*channels");
+    const size_t pitch = in_row_pitch ? in_row_pitch : row_bytes;
     const uint8_t *base = static_cast<const uint8_t *>(in);
     memset(l, 0, sizeof *l);
     l->in = base ? base + (size_t)first_row * pitch : nullptr;
@@ -702,6 +754,8 @@ int b200blur_launch_rows(b200blur_launch *l, const void *in, void *out, int widt
     l->n_images = n_images;
     l->in_image_stride = in_image_stride;
     l->out_image_stride = out_image_stride;
+    l->in_row_pitch = in_row_pitch;
+    l->out_row_pitch = out_row_pitch;
     if (base && n_rows > 0 && first_row > 0) {
         l->halo_top = base + (size_t)(first_row - 1) * pitch;
         l->halo_top_stride = in_image_stride;
@@ -711,6 +765,14 @@ int b200blur_launch_rows(b200blur_launch *l, const void *in, void *out, int widt
         l->halo_bottom_stride = in_image_stride;
     }
     return B200BLUR_OK;
+}
+
+int b200blur_launch_rows(b200blur_launch *l, const void *in, void *out, int width, int in_height, int channels,
+                         int first_row, int n_rows, int64_t n_images, size_t in_image_stride,
+                         size_t out_image_stride)
+{
+    return b200blur_launch_rows_pitched(l, in, out, width, in_height, channels, first_row, n_rows, n_images,
+                                        in_image_stride, out_image_stride, 0, 0);
 }
 
 int b200blur_launch_is_vectorised(const b200blur_launch *launch)
@@ -787,6 +849,53 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
     if (stats)
         if (int rc = event_begin(ctx, 0, &ev_all, &slot)) return rc;
     int64_t launches = 0;
+    // Odd widths (width*channels % 16 != 0): tight rows cannot be read 16 bytes at a time, so the stream is re-pitched
+    // through a scratch pair with strided device copies, ~128 MB at a time, and blurred on the vectorised path
+    // (3 passes over the data instead of the ~20x slower byte-wise generic kernel).
+    const size_t row_bytes = (size_t)width * channels;
+    if (row_bytes % 16 != 0 && channels <= 4 && row_bytes >= 256 && n_images > 0 && height > 0) {
+        const size_t dev_pitch = (row_bytes + 15) / 16 * 16;
+        const size_t dev_image_bytes = dev_pitch * (size_t)height;
+        int64_t chunk = (int64_t)((128ull << 20) / dev_image_bytes);
+        if (chunk < 1) chunk = 1;
+        if (chunk > n_images) chunk = n_images;
+        const size_t need = dev_image_bytes * (size_t)chunk;
+        if (ctx->scratch_bytes < need) {
+            if (ctx->scratch_in) cudaFree(ctx->scratch_in);
+            if (ctx->scratch_out) cudaFree(ctx->scratch_out);
+            ctx->scratch_in = ctx->scratch_out = nullptr;
+            ctx->scratch_bytes = 0;
+            CU_TRY(cudaMalloc((void **)&ctx->scratch_in, need));
+            CU_TRY(cudaMalloc((void **)&ctx->scratch_out, need));
+            ctx->scratch_bytes = need;
+        }
+        for (int64_t i0 = 0; i0 < n_images; i0 += chunk) {
+            const int64_t n = (n_images - i0 < chunk) ? n_images - i0 : chunk;
+            CU_TRY(cudaMemcpy2DAsync(ctx->scratch_in, dev_pitch, static_cast<const uint8_t *>(d_in) + (size_t)i0 * image_bytes,
+                                     row_bytes, row_bytes, (size_t)n * height, cudaMemcpyDeviceToDevice, s));
+            b200blur_launch l;
+            if (int rc = b200blur_launch_rows_pitched(&l, ctx->scratch_in, ctx->scratch_out, width, height, channels, 0,
+                                                      height, n, dev_image_bytes, dev_image_bytes, dev_pitch, dev_pitch))
+                return rc;
+            int nk;
+            if (int rc = do_launch(ctx, 0, &l, &nk)) return rc;
+            launches += nk;
+            CU_TRY(cudaMemcpy2DAsync(static_cast<uint8_t *>(d_out) + (size_t)i0 * image_bytes, row_bytes, ctx->scratch_out,
+                                     dev_pitch, row_bytes, (size_t)n * height, cudaMemcpyDeviceToDevice, s));
+        }
+        if (stats) {
+            if (int rc = event_end(ctx, 0, slot)) return rc;
+            double ms = 0;
+            if (int rc = b200blur_event_ms(ctx, ev_all, &ms)) return rc;
+            b200blur_event_release(ctx, ev_all);
+            memset(stats, 0, sizeof *stats);
+            stats->kernel_ms = ms;
+            stats->images = n_images;
+            stats->launches = launches;
+            stats->wall_ms = now_ms() - t0;
+        }
+        return B200BLUR_OK;
+    }
     const int64_t step = coalesce ? (n_images > 0 ? n_images : 1) : batch_size;
     // One launch per batch (coalesce == 0): the batches are independent, so their launches are spread round-robin
     // over all queues of the context and overlap each other's ramp-up and tail; queue 0 forks and joins the others,
@@ -926,7 +1035,13 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
         if (chunk > 0x7fffffffLL) chunk = 0x7fffffffLL;
         batch_size = (int)chunk;
     }
-    if (int rc = ring_prepare(ctx, image_bytes * (size_t)batch_size, n_slots)) return rc;
+    // Odd widths (width*channels % 16 != 0): the strided copy engine re-pitches rows to a multiple of 16 bytes on the
+    // way in and back on the way out, so the vectorised kernel runs on any image width.
+    const size_t row_bytes = (size_t)width * channels;
+    const bool repitch = row_bytes % 16 != 0 && channels <= 4 && row_bytes >= 256;
+    const size_t dev_pitch = repitch ? (row_bytes + 15) / 16 * 16 : row_bytes;
+    const size_t dev_image_bytes = dev_pitch * (size_t)height;
+    if (int rc = ring_prepare(ctx, dev_image_bytes * (size_t)batch_size, n_slots)) return rc;
     cudaStream_t q_in = ctx->queues[0], q_k = ctx->queues[1], q_out = ctx->queues[2];
     const double t0 = now_ms();
     double ms_in = 0, ms_k = 0, ms_out = 0;
@@ -949,18 +1064,22 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
         const int64_t i0 = ci * batch_size;
         const int64_t n = (n_images - i0 < batch_size) ? n_images - i0 : batch_size;
         const size_t bytes = (size_t)n * image_bytes;
+        const uint8_t *src = static_cast<const uint8_t *>(h_in) + (size_t)i0 * image_bytes;
+        uint8_t *dst = static_cast<uint8_t *>(h_out) + (size_t)i0 * image_bytes;
         // H2D
         CU_TRY(cudaEventRecord(s.ev[0], q_in));
-        if (bytes)
-            CU_TRY(cudaMemcpyAsync(s.d_in, static_cast<const uint8_t *>(h_in) + (size_t)i0 * image_bytes, bytes,
-                                   cudaMemcpyHostToDevice, q_in));
+        if (bytes && !repitch) CU_TRY(cudaMemcpyAsync(s.d_in, src, bytes, cudaMemcpyHostToDevice, q_in));
+        if (bytes && repitch)
+            CU_TRY(cudaMemcpy2DAsync(s.d_in, dev_pitch, src, row_bytes, row_bytes, (size_t)n * height,
+                                     cudaMemcpyHostToDevice, q_in));
         CU_TRY(cudaEventRecord(s.ev[1], q_in));
         // blur
         CU_TRY(cudaStreamWaitEvent(q_k, s.ev[1], 0));
         CU_TRY(cudaEventRecord(s.ev[2], q_k));
         b200blur_launch l;
-        if (int rc = b200blur_launch_rows(&l, s.d_in, s.d_out, width, height, channels, 0, height, n, image_bytes,
-                                          image_bytes))
+        if (int rc = b200blur_launch_rows_pitched(&l, s.d_in, s.d_out, width, height, channels, 0, height, n,
+                                                  dev_image_bytes, dev_image_bytes, repitch ? dev_pitch : 0,
+                                                  repitch ? dev_pitch : 0))
             return rc;
         int nk;
         if (int rc = do_launch(ctx, 1, &l, &nk)) return rc;
@@ -969,9 +1088,10 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
         // D2H
         CU_TRY(cudaStreamWaitEvent(q_out, s.ev[3], 0));
         CU_TRY(cudaEventRecord(s.ev[4], q_out));
-        if (bytes)
-            CU_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(h_out) + (size_t)i0 * image_bytes, s.d_out, bytes,
-                                   cudaMemcpyDeviceToHost, q_out));
+        if (bytes && !repitch) CU_TRY(cudaMemcpyAsync(dst, s.d_out, bytes, cudaMemcpyDeviceToHost, q_out));
+        if (bytes && repitch)
+            CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, s.d_out, dev_pitch, row_bytes, (size_t)n * height,
+                                     cudaMemcpyDeviceToHost, q_out));
         CU_TRY(cudaEventRecord(s.ev[5], q_out));
     }
     const int64_t first_pending = n_chunks > n_slots ? n_chunks - n_slots : 0;

@@ -27,7 +27,9 @@ struct BandParams {
     size_t out_stride;
     size_t top_stride;
     size_t bot_stride;
-    int pitch;                // bytes per row = width * channels
+    int pitch;                // bytes between rows of `in` (>= row_bytes; the vectorised kernels need pitch % 16 == 0)
+    int out_pitch;            // bytes between rows of `out`
+    int row_bytes;            // meaningful bytes per row = width * channels
     int rows;                 // band height (rows computed and stored)
     int width;
     int channels;
@@ -197,7 +199,7 @@ blur_strip_kernel(const BandParams p, int cpr, int n_strips)
             o.y = vpass_word(h2E[1], h1E[1], hE[1], h2O[1], h1O[1], hO[1]);
             o.z = vpass_word(h2E[2], h1E[2], hE[2], h2O[2], h1O[2], hO[2]);
             o.w = vpass_word(h2E[3], h1E[3], hE[3], h2O[3], h1O[3], hO[3]);
-            if (valid && r < p.rows) stg128_stream(dst + (size_t)r * p.pitch, o);
+            if (valid && r < p.rows) stg128_stream(dst + (size_t)r * p.out_pitch, o);
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -232,6 +234,14 @@ struct StreamParams {
     long long img_blocks;   // ceil(n_images / ipc)
     long long n_groups;     // img_blocks * nseg * ncb
     unsigned long long *work;  // work[0] = next group to hand out, work[1] = CTAs finished (both 0 between launches)
+    // Right edge of a row that does not end on a chunk boundary (row_bytes % 16 != 0, pitched rows).  The clamp
+    // "pixel width := pixel width-1" means window bytes [row_bytes, row_bytes + C) := bytes [row_bytes - C, row_bytes).
+    // For the chunk that contains the row end (and the one before it when the end is < 4 bytes into the last chunk)
+    // the 24-byte window {wl, w, wr} is rewritten with one PRMT per word; the selectors are computed on the host.
+    int edge_general;          // 0: rows end on a chunk boundary (fast path)
+    int edge_prev;             // 1: the chunk before the last one needs its wr word patched too
+    uint32_t sel_last[6];      // PRMT selectors for window words 0..5 of the last chunk (pairs: previous word, word)
+    uint32_t sel_prev;         // PRMT selector for the wr word of the chunk before the last
 };
 
 namespace ptx {
@@ -291,6 +301,7 @@ struct GroupGeom {
     int r0;           // first output row
     int nr;           // output rows
     int x0;           // first byte column of the column block
+    int chunk0;       // index of its first chunk within the row
     int cbe;          // chunks in this column block
     bool left_edge, right_edge;
 };
@@ -308,6 +319,7 @@ __device__ __forceinline__ GroupGeom decode_group(const StreamParams &sp, long l
     q.r0 = si * sp.seg;
     q.nr = min(sp.seg, sp.b.rows - q.r0);
     q.x0 = ci * sp.cb * 16;
+    q.chunk0 = ci * sp.cb;
     q.cbe = min(sp.cb, sp.cpr - ci * sp.cb);
     q.left_edge = (ci == 0);
     q.right_edge = (ci == sp.ncb - 1);
@@ -344,7 +356,9 @@ __device__ __forceinline__ void stream_issue_slot(const StreamParams &sp, const 
                 rp = src + (size_t)j * b.pitch;
                 if (sp.margin == 0) run = min(k1 - k, b.rows - j);  // contiguous rows: one copy
             }
-            const uint32_t bytes = (sp.margin == 0) ? (uint32_t)run * (uint32_t)b.pitch : row_bytes;
+            // full-width: `run` whole rows as they lie in memory (padding included); a halo row brings only its live chunks
+            const uint32_t bytes = (sp.margin != 0) ? row_bytes
+                                   : (j < 0 || j >= b.rows) ? (uint32_t)sp.cpr * 16u : (uint32_t)run * (uint32_t)b.pitch;
             const uint32_t dst = dst_img + (uint32_t)((k - k0) * sp.sstride) + dst_col;
             ptx::mbar_expect_tx(bar, bytes);
             ptx::bulk_g2s(dst, rp + xb, bytes, bar);
@@ -360,7 +374,8 @@ __device__ __forceinline__ void stream_issue_slot(const StreamParams &sp, const 
 // Work is handed out dynamically: the producer takes the next group from a global atomic counter and publishes its
 // index next to the slot (meta[]), so SMs that see more bandwidth simply take more groups.  (A static round-robin
 // persistent grid loses ~10 % of HBM bandwidth on B200 -- tools/membench.cu, profiles/membench_r01.txt.)
-template <int C, int RB, int NS>
+// EDGE = rows that do not end on a chunk boundary (pitched rows); compiled separately so the aligned case pays nothing.
+template <int C, int RB, int NS, bool EDGE = false>
 __global__ void __launch_bounds__(32 + 256)
 blur_stream_kernel(const StreamParams sp)
 {
@@ -428,14 +443,15 @@ blur_stream_kernel(const StreamParams sp)
         const GroupGeom q = decode_group(sp, g);
         const bool active = (il < q.n_img) && (c < q.cbe);
         const bool first = q.left_edge && (c == 0);
-        const bool last = q.right_edge && (c == q.cbe - 1);
+        const bool last = q.right_edge && (c == q.cbe - 1);               // the chunk that holds the end of the row
+        const bool prev_last = EDGE && sp.edge_prev && (q.chunk0 + c == sp.cpr - 2);
         const int nslots = (q.nr + 2 + RB - 1) / RB;
         const int il_c = active ? il : 0, c_c = active ? c : 0;
         const uint32_t lane_off = (uint32_t)(il_c * RB * sp.sstride + sp.margin + c_c * 16);
         // Output row k-2 is produced when input row k of the item arrives; the store pointer starts two rows early
         // and advances every row so the loop body has no branches (stores for k < 2 and k >= nr+2 are predicated off).
-        uint8_t *dst = sp.b.out + (size_t)(q.img0 + il_c) * sp.b.out_stride + (size_t)q.r0 * sp.b.pitch + q.x0 + c_c * 16 -
-                       2 * (ptrdiff_t)sp.b.pitch;
+        uint8_t *dst = sp.b.out + (size_t)(q.img0 + il_c) * sp.b.out_stride + (size_t)q.r0 * sp.b.out_pitch + q.x0 + c_c * 16 -
+                       2 * (ptrdiff_t)sp.b.out_pitch;
         // Rolling vertical state, pre-scaled by 16: before row k arrives
         //   accA = 16*(h[k-2] + 2*h[k-1])   accB = 16*h[k-1]        (<= 48960 per 16-bit lane)
         uint32_t accA[8], accB[8];
@@ -450,12 +466,21 @@ blur_stream_kernel(const StreamParams sp)
 #pragma unroll
             for (int r = 0; r < RB; r++) {
                 if (k >= k_end) break;                  // short last slot of an item (uniform across the CTA)
-                const uint4 w = ptx::lds128(a);
+                uint4 w = ptx::lds128(a);
                 uint32_t wl = ptx::lds32(a - 4);
                 uint32_t wr = ptx::lds32(a + 16);
                 a += sp.sstride;
                 if (first) wl = w.x << (8 * (4 - C));   // clamp: pixel -1 := pixel 0        (gaussian_kernel.cl:56)
-                if (last) wr = w.w >> (8 * (4 - C));    // clamp: pixel width := pixel width-1
+                if (!EDGE) {
+                    if (last) wr = w.w >> (8 * (4 - C));    // clamp: pixel width := pixel width-1
+                } else if (last) {                          // row ends inside this chunk: rewrite the window
+                    const uint32_t n0 = __byte_perm(wl, w.x, sp.sel_last[1]), n1 = __byte_perm(w.x, w.y, sp.sel_last[2]);
+                    const uint32_t n2 = __byte_perm(w.y, w.z, sp.sel_last[3]), n3 = __byte_perm(w.z, w.w, sp.sel_last[4]);
+                    wr = __byte_perm(w.w, wr, sp.sel_last[5]);
+                    w.x = n0; w.y = n1; w.z = n2; w.w = n3;
+                } else if (prev_last) {
+                    wr = __byte_perm(w.w, wr, sp.sel_prev);
+                }
                 uint32_t h[8];
                 hpass8<C>(w, wl, wr, h);
                 uint32_t v[8];
@@ -471,7 +496,7 @@ blur_stream_kernel(const StreamParams sp)
                 o.z = __byte_perm(v[4], v[5], 0x7351);
                 o.w = __byte_perm(v[6], v[7], 0x7351);
                 if (active && k >= 2) stg128_stream(dst, o);
-                dst += sp.b.pitch;
+                dst += sp.b.out_pitch;
                 k++;
             }
             __syncwarp();
@@ -486,14 +511,14 @@ blur_stream_kernel(const StreamParams sp)
 __global__ void __launch_bounds__(256)
 blur_generic_kernel(const BandParams p)
 {
-    const long long per_image = (long long)p.rows * p.pitch;
+    const long long per_image = (long long)p.rows * p.row_bytes;
     const long long total = per_image * p.n_images;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += step) {
         const long long img = g / per_image;
         const int rem = (int)(g - img * per_image);
-        const int r = rem / p.pitch;
-        const int b = rem - r * p.pitch;
+        const int r = rem / p.row_bytes;
+        const int b = rem - r * p.row_bytes;
         const int x = b / p.channels;
         const int bl = (x > 0) ? b - p.channels : b;
         const int br = (x < p.width - 1) ? b + p.channels : b;
@@ -506,7 +531,7 @@ blur_generic_kernel(const BandParams p)
         const int hu = up[bl] + 2 * up[b] + up[br];
         const int hm = mid[bl] + 2 * mid[b] + mid[br];
         const int hd = dn[bl] + 2 * dn[b] + dn[br];
-        p.out[(size_t)img * p.out_stride + (size_t)r * p.pitch + b] = (uint8_t)((hu + 2 * hm + hd) >> 4);
+        p.out[(size_t)img * p.out_stride + (size_t)r * p.out_pitch + b] = (uint8_t)((hu + 2 * hm + hd) >> 4);
     }
 }
 

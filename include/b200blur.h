@@ -129,8 +129,9 @@ B200BLUR_API int b200blur_finish_all(b200blur_ctx *ctx);
  * for out / halo_top / halo_bottom with their own strides.  Halo pointers may address another GPU's memory
  * (peer-enabled or IPC-opened): the kernel then loads those rows over NVLink itself -- that is Approach 2's
  * halo exchange fused into the stencil.
- * in == out (in place) is not allowed.  The vectorised path needs width*channels % 16 == 0, channels <= 4 and
- * 16-byte aligned pointers/strides; anything else runs the generic path (same results).
+ * in == out (in place) is not allowed.  The vectorised path needs channels <= 4, 16-byte aligned pointers/strides
+ * and a row pitch that is a multiple of 16 (tight rows with width*channels % 16 == 0, or in/out_row_pitch set);
+ * anything else runs the generic path (same results).
  */
 typedef struct b200blur_launch {
     const void *in;
@@ -146,6 +147,12 @@ typedef struct b200blur_launch {
     size_t halo_top_stride;
     const void *halo_bottom;
     size_t halo_bottom_stride;
+    /* Row pitch in bytes of `in` / `out` (0 = tight, width*channels).  A pitch that is a multiple of 16 lets ANY width
+     * run on the vectorised path: bytes between width*channels and the pitch are padding (read, never meaningful;
+     * the output's padding is overwritten with don't-care bytes).  The stream engines use this to re-pitch odd-width
+     * images with strided copies.  Halo rows are single rows and have no pitch. */
+    size_t in_row_pitch;
+    size_t out_row_pitch;
 } b200blur_launch;
 
 /* Fill a launch that is exactly "the reference kernel with height = in_height on buffer `in`, keeping output rows
@@ -157,6 +164,12 @@ typedef struct b200blur_launch {
 B200BLUR_API int b200blur_launch_rows(b200blur_launch *l, const void *in, void *out, int width, int in_height,
                                       int channels, int first_row, int n_rows, int64_t n_images,
                                       size_t in_image_stride, size_t out_image_stride);
+
+/* Same with explicit row pitches (0 = tight): rows of `in` are in_row_pitch bytes apart, rows of `out` out_row_pitch. */
+B200BLUR_API int b200blur_launch_rows_pitched(b200blur_launch *l, const void *in, void *out, int width, int in_height,
+                                              int channels, int first_row, int n_rows, int64_t n_images,
+                                              size_t in_image_stride, size_t out_image_stride, size_t in_row_pitch,
+                                              size_t out_row_pitch);
 
 /* clSetKernelArg x5 + clEnqueueNDRangeKernel (A1:366-389, :507): asynchronous, in order on `queue`. */
 B200BLUR_API int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200blur_launch *launch,

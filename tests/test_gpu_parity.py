@@ -271,6 +271,58 @@ def test_no_writes_outside_the_output_range(ctx, shape):
     assert_same(back[guard:guard + x.nbytes].reshape(shape), oracle.c_blur_batch(x))
 
 
+def _blur_pitched(ctx, x, extra_pitch=0):
+    """Upload tight host rows into 16-byte-pitched device rows with a strided copy, blur with row pitches, read back."""
+    n, h, w, c = x.shape
+    P = w * c
+    pitch = (P + 15) // 16 * 16 + extra_pitch
+    d_in, d_out = ctx.dev_alloc(n * h * pitch + 64), ctx.dev_alloc(n * h * pitch + 64)
+    ctx.enqueue_write_2d(0, d_in, pitch, x, P, P, n * h)
+    l = ctx.launch_rows(d_in, d_out, w, h, c, 0, h, n, in_row_pitch=pitch, out_row_pitch=pitch)
+    assert l.in_image_stride == pitch * h and ctx.is_vectorised(l)
+    ctx.enqueue_blur(0, l)
+    out = np.zeros_like(x)
+    ctx.enqueue_read_2d(0, out, P, d_out, pitch, P, n * h)
+    ctx.finish()
+    ctx.dev_free(d_in)
+    ctx.dev_free(d_out)
+    return out
+
+
+@pytest.mark.parametrize("shape", [(3, 37, 250, 3), (2, 20, 100, 3), (4, 9, 86, 3), (2, 64, 341, 3), (2, 5, 1366, 3),
+                                   (3, 33, 257, 1), (2, 17, 130, 2), (2, 12, 67, 4), (1, 8, 1370, 3), (2, 7, 91, 3)])
+def test_pitched_rows_run_any_width_on_the_vectorised_path(ctx, shape):
+    """Rows re-pitched to a multiple of 16 bytes: the row end falls inside a chunk, so the right-edge clamp is applied by
+    per-launch PRMT selectors (also when the last pixel straddles two chunks: 86*3 = 258 = 16*16 + 2)."""
+    n, h, w, c = shape
+    x = synth(sum(shape) * 3, n, h, w, c)
+    want = oracle.c_blur_batch(x)
+    assert_same(_blur_pitched(ctx, x), want)
+    assert_same(_blur_pitched(ctx, x, extra_pitch=48), want)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(300, 37, 250, 3), (40, 100, 341, 3), (3, 700, 1366, 3)])
+def test_run_resident_repitches_odd_widths(ctx, n, h, w, c):
+    import torch
+    x = synth(n * 7 + w, n, h, w, c)
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    st = ctx.run_resident(d_in, d_out, w, h, c, n, 35, True)
+    torch.cuda.synchronize()
+    assert st.images == n and st.launches >= 1
+    assert_same(d_out.cpu().numpy(), oracle.c_blur_batch(x, integer=True))
+
+
+@pytest.mark.parametrize("n,h,w,c,batch", [(60, 37, 250, 3, 7), (20, 50, 341, 3, 35), (10, 16, 1366, 3, 4), (8, 20, 300, 1, 3)])
+def test_run_host_repitches_odd_widths(ctx, n, h, w, c, batch):
+    x = synth(n + h + w, n, h, w, c)
+    out = np.zeros_like(x)
+    st = ctx.run_host(x, out, w, h, c, n, batch)
+    assert st.images == n
+    assert_same(out, oracle.c_blur_batch(x, integer=True))
+
+
 def test_image_strides_larger_than_image(ctx):
     n, h, w, c = 3, 12, 32, 3
     img_bytes = h * w * c
