@@ -210,7 +210,8 @@ typedef struct b200blur_stats {
  * (they are independent), otherwise one launch per batch like the reference's per-batch sync (A1:538).  In the
  * per-batch form the launches are spread over ALL queues of the context (forked from and joined back into queue 0,
  * so the call still orders like one operation on queue 0) and a repeated identical request is replayed as a CUDA
- * graph.  stats == NULL makes the call asynchronous (no host synchronisation). */
+ * graph.  stats == NULL makes the call asynchronous (no host synchronisation).  Widths with width*channels % 16 != 0
+ * are re-pitched through a scratch pair owned by the context so that they still run on the vectorised kernel. */
 B200BLUR_API int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int width, int height,
                                        int channels, int64_t n_images, int batch_size, int coalesce,
                                        b200blur_stats *stats);
@@ -218,7 +219,7 @@ B200BLUR_API int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void
  * `batch_size` images flow H2D -> blur -> D2H through a ring of device buffers on separate queues so the three
  * stages of different chunks overlap (the reference serialises them per image).  Batches are
  * independent, so small batches are fused (and very large ones cut) into ~64 MB transfer chunks; stats->launches
- * reports the kernels actually launched. */
+ * reports the kernels actually launched.  Odd widths are re-pitched by the strided copies on the way in and out. */
 B200BLUR_API int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int width, int height,
                                    int channels, int64_t n_images, int batch_size, b200blur_stats *stats);
 
