@@ -67,10 +67,11 @@ struct b200blur_ctx {
     // ring of device buffers owned by b200blur_run_host
     struct Slot {
         uint8_t *d_in = nullptr, *d_out = nullptr;
+        uint8_t *t_in = nullptr, *t_out = nullptr;  // tight staging for odd widths (re-pitched on the device)
         cudaEvent_t ev[6] = {};  // h2d start/end, kernel start/end, d2h start/end
     };
     std::vector<Slot> ring;
-    size_t ring_slot_bytes = 0;
+    size_t ring_slot_bytes = 0, ring_tight_bytes = 0;
     // work counters of the streamed kernel: two 64-bit words per queue, zero between launches
     unsigned long long *d_work = nullptr;
     // per-kernel launch facts (max dynamic smem attribute set, resident CTAs/SM), cached: both calls are slow
@@ -392,6 +393,33 @@ int do_launch(b200blur_ctx *ctx, int queue, const b200blur_launch *l, int *n_ker
     return B200BLUR_OK;
 }
 
+// tight <-> pitched row re-packing on stream s (see repitch_*_kernel); both pointers 16-byte aligned
+void launch_repitch_in(b200blur_ctx *ctx, cudaStream_t s, const void *tight, void *pitched, long long rows, int row_bytes, int pitch)
+{
+    const long long total = rows * ((row_bytes + 15) / 16);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    b200blur::repitch_in_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const uint8_t *>(tight), static_cast<uint8_t *>(pitched),
+                                                                 rows, row_bytes, pitch);
+    ctx->launches++;
+}
+
+// `tight_base` is 16-byte aligned; the rows land at byte offset `lo` of it
+void launch_repitch_out(b200blur_ctx *ctx, cudaStream_t s, const void *pitched, void *tight_base, long long lo, long long rows,
+                        int row_bytes, int pitch)
+{
+    const long long total = (rows * (long long)row_bytes + 15) / 16 + 1;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    b200blur::repitch_out_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const uint8_t *>(pitched),
+                                                                  static_cast<uint8_t *>(tight_base), lo, rows, row_bytes, pitch);
+    ctx->launches++;
+}
+
 double now_ms()
 {
     using namespace std::chrono;
@@ -492,11 +520,14 @@ static void ring_release(b200blur_ctx *ctx)
     for (auto &s : ctx->ring) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
+        if (s.t_in) cudaFree(s.t_in);
+        if (s.t_out) cudaFree(s.t_out);
         for (auto &e : s.ev)
             if (e) cudaEventDestroy(e);
     }
     ctx->ring.clear();
     ctx->ring_slot_bytes = 0;
+    ctx->ring_tight_bytes = 0;
 }
 
 int b200blur_ctx_destroy(b200blur_ctx *ctx)
@@ -871,8 +902,16 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
         }
         for (int64_t i0 = 0; i0 < n_images; i0 += chunk) {
             const int64_t n = (n_images - i0 < chunk) ? n_images - i0 : chunk;
-            CU_TRY(cudaMemcpy2DAsync(ctx->scratch_in, dev_pitch, static_cast<const uint8_t *>(d_in) + (size_t)i0 * image_bytes,
-                                     row_bytes, row_bytes, (size_t)n * height, cudaMemcpyDeviceToDevice, s));
+            const uint8_t *src = static_cast<const uint8_t *>(d_in) + (size_t)i0 * image_bytes;
+            uint8_t *dst = static_cast<uint8_t *>(d_out) + (size_t)i0 * image_bytes;
+            const bool fast_repack = aligned16(d_out);  // the re-pack kernel writes aligned 16-byte words of the tight output
+            if (fast_repack) {
+                launch_repitch_in(ctx, s, src, ctx->scratch_in, n * (long long)height, (int)row_bytes, (int)dev_pitch);
+                launches++;
+            } else {
+                CU_TRY(cudaMemcpy2DAsync(ctx->scratch_in, dev_pitch, src, row_bytes, row_bytes, (size_t)n * height,
+                                         cudaMemcpyDeviceToDevice, s));
+            }
             b200blur_launch l;
             if (int rc = b200blur_launch_rows_pitched(&l, ctx->scratch_in, ctx->scratch_out, width, height, channels, 0,
                                                       height, n, dev_image_bytes, dev_image_bytes, dev_pitch, dev_pitch))
@@ -880,8 +919,14 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
             int nk;
             if (int rc = do_launch(ctx, 0, &l, &nk)) return rc;
             launches += nk;
-            CU_TRY(cudaMemcpy2DAsync(static_cast<uint8_t *>(d_out) + (size_t)i0 * image_bytes, row_bytes, ctx->scratch_out,
-                                     dev_pitch, row_bytes, (size_t)n * height, cudaMemcpyDeviceToDevice, s));
+            if (fast_repack) {
+                launch_repitch_out(ctx, s, ctx->scratch_out, d_out, (long long)((size_t)i0 * image_bytes), n * (long long)height,
+                                   (int)row_bytes, (int)dev_pitch);
+                launches++;
+            } else {
+                CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, ctx->scratch_out, dev_pitch, row_bytes, (size_t)n * height,
+                                         cudaMemcpyDeviceToDevice, s));
+            }
         }
         if (stats) {
             if (int rc = event_end(ctx, 0, slot)) return rc;
@@ -985,17 +1030,23 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
     return B200BLUR_OK;
 }
 
-static int ring_prepare(b200blur_ctx *ctx, size_t slot_bytes, int n_slots)
+static int ring_prepare(b200blur_ctx *ctx, size_t slot_bytes, size_t tight_bytes, int n_slots)
 {
-    if (ctx->ring_slot_bytes >= slot_bytes && (int)ctx->ring.size() == n_slots) return B200BLUR_OK;
+    if (ctx->ring_slot_bytes >= slot_bytes && ctx->ring_tight_bytes >= tight_bytes && (int)ctx->ring.size() == n_slots)
+        return B200BLUR_OK;
     ring_release(ctx);
     ctx->ring.resize(n_slots);
     for (auto &s : ctx->ring) {
         CU_TRY(cudaMalloc((void **)&s.d_in, slot_bytes ? slot_bytes : 16));
         CU_TRY(cudaMalloc((void **)&s.d_out, slot_bytes ? slot_bytes : 16));
+        if (tight_bytes) {
+            CU_TRY(cudaMalloc((void **)&s.t_in, tight_bytes + 16));
+            CU_TRY(cudaMalloc((void **)&s.t_out, tight_bytes + 16));
+        }
         for (auto &e : s.ev) CU_TRY(cudaEventCreate(&e));
     }
     ctx->ring_slot_bytes = slot_bytes;
+    ctx->ring_tight_bytes = tight_bytes;
     return B200BLUR_OK;
 }
 
@@ -1035,13 +1086,15 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
         if (chunk > 0x7fffffffLL) chunk = 0x7fffffffLL;
         batch_size = (int)chunk;
     }
-    // Odd widths (width*channels % 16 != 0): the strided copy engine re-pitches rows to a multiple of 16 bytes on the
-    // way in and back on the way out, so the vectorised kernel runs on any image width.
+    // Odd widths (width*channels % 16 != 0): rows travel tight over the host link (linear copies at link speed; the
+    // copy engines' strided copies manage only 6.5 GB/s on 750-byte rows) and are re-pitched to a multiple of 16 bytes
+    // on the device by two small kernels around the blur, so the vectorised kernel runs on any image width.
     const size_t row_bytes = (size_t)width * channels;
     const bool repitch = row_bytes % 16 != 0 && channels <= 4 && row_bytes >= 256;
     const size_t dev_pitch = repitch ? (row_bytes + 15) / 16 * 16 : row_bytes;
     const size_t dev_image_bytes = dev_pitch * (size_t)height;
-    if (int rc = ring_prepare(ctx, dev_image_bytes * (size_t)batch_size, n_slots)) return rc;
+    if (int rc = ring_prepare(ctx, dev_image_bytes * (size_t)batch_size, repitch ? image_bytes * (size_t)batch_size : 0, n_slots))
+        return rc;
     cudaStream_t q_in = ctx->queues[0], q_k = ctx->queues[1], q_out = ctx->queues[2];
     const double t0 = now_ms();
     double ms_in = 0, ms_k = 0, ms_out = 0;
@@ -1068,10 +1121,7 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
         uint8_t *dst = static_cast<uint8_t *>(h_out) + (size_t)i0 * image_bytes;
         // H2D
         CU_TRY(cudaEventRecord(s.ev[0], q_in));
-        if (bytes && !repitch) CU_TRY(cudaMemcpyAsync(s.d_in, src, bytes, cudaMemcpyHostToDevice, q_in));
-        if (bytes && repitch)
-            CU_TRY(cudaMemcpy2DAsync(s.d_in, dev_pitch, src, row_bytes, row_bytes, (size_t)n * height,
-                                     cudaMemcpyHostToDevice, q_in));
+        if (bytes) CU_TRY(cudaMemcpyAsync(repitch ? s.t_in : s.d_in, src, bytes, cudaMemcpyHostToDevice, q_in));
         CU_TRY(cudaEventRecord(s.ev[1], q_in));
         // blur
         CU_TRY(cudaStreamWaitEvent(q_k, s.ev[1], 0));
@@ -1081,17 +1131,23 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
                                                   dev_image_bytes, dev_image_bytes, repitch ? dev_pitch : 0,
                                                   repitch ? dev_pitch : 0))
             return rc;
+        if (repitch && bytes) {
+            launch_repitch_in(ctx, q_k, s.t_in, s.d_in, n * (long long)height, (int)row_bytes, (int)dev_pitch);
+            launches++;
+        }
         int nk;
         if (int rc = do_launch(ctx, 1, &l, &nk)) return rc;
         launches += nk;
+        if (repitch && bytes) {
+            launch_repitch_out(ctx, q_k, s.d_out, s.t_out, 0, n * (long long)height, (int)row_bytes, (int)dev_pitch);
+            launches++;
+        }
+        CU_TRY(cudaGetLastError());
         CU_TRY(cudaEventRecord(s.ev[3], q_k));
         // D2H
         CU_TRY(cudaStreamWaitEvent(q_out, s.ev[3], 0));
         CU_TRY(cudaEventRecord(s.ev[4], q_out));
-        if (bytes && !repitch) CU_TRY(cudaMemcpyAsync(dst, s.d_out, bytes, cudaMemcpyDeviceToHost, q_out));
-        if (bytes && repitch)
-            CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, s.d_out, dev_pitch, row_bytes, (size_t)n * height,
-                                     cudaMemcpyDeviceToHost, q_out));
+        if (bytes) CU_TRY(cudaMemcpyAsync(dst, repitch ? s.t_out : s.d_out, bytes, cudaMemcpyDeviceToHost, q_out));
         CU_TRY(cudaEventRecord(s.ev[5], q_out));
     }
     const int64_t first_pending = n_chunks > n_slots ? n_chunks - n_slots : 0;
