@@ -439,6 +439,24 @@ def test_full_size_stream_properties(ctx):
     assert_same(whole[idx].cpu().numpy(), oracle.c_blur_batch(sample, integer=True))
 
 
+def test_stream_larger_than_4_gib_uses_64_bit_offsets(ctx):
+    """24,000 x 256x256 RGB = 4.7 GB per direction (> 2^32 bytes; BASELINE configs[3] goes to 9.8 GB): every slot of a
+    replicated stream must equal the oracle's image, which catches any 32-bit offset in the kernels or the launchers."""
+    import torch
+    n, h, w, c = 24000, 256, 256, 3
+    one = synth(41, 1, h, w, c)
+    want = torch.from_numpy(oracle.c_blur(one[0])).cuda()
+    d_in = torch.from_numpy(one).cuda().expand(n, h, w, c).contiguous()
+    d_out = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    ctx.run_resident(d_in, d_out, w, h, c, n, 1200, True)
+    torch.cuda.synchronize()
+    for lo in range(0, n, 4000):     # compare in slices to bound the temporary
+        assert bool((d_out[lo:lo + 4000] == want[None]).all()), lo
+    del d_in, d_out
+    torch.cuda.empty_cache()
+
+
 def test_large_frame(ctx):
     """One 8192x8192 RGB frame (BASELINE configs[4] shape): bands of 1024 rows == whole image, sample rows == oracle."""
     import torch
