@@ -305,15 +305,17 @@ struct GroupGeom {
     int cbe;          // chunks in this column block
     bool left_edge, right_edge;
 };
-__device__ __forceinline__ GroupGeom decode_group(const StreamParams &sp, long long g)
+__device__ __forceinline__ GroupGeom decode_group(const StreamParams &sp, long long g64)
 {
     GroupGeom q;
-    const int per_block = sp.nseg * sp.ncb;
-    const long long ib = g / per_block;
+    // n_groups < 2^31 (checked on the host: a group is at least a few KB), so 32-bit division -- inlined, no call
+    const unsigned g = (unsigned)g64;
+    const unsigned per_block = (unsigned)(sp.nseg * sp.ncb);
+    const unsigned ib = g / per_block;
     const int sc = (int)(g - ib * per_block);
     const int si = sc / sp.ncb;
     const int ci = sc - si * sp.ncb;
-    q.img0 = ib * sp.ipc;
+    q.img0 = (long long)ib * sp.ipc;
     const long long left = sp.b.n_images - q.img0;
     q.n_img = left < sp.ipc ? (int)left : sp.ipc;
     q.r0 = si * sp.seg;
