@@ -348,8 +348,37 @@ def run_b200_arm(args) -> None:
     e2e_launches = ctx.launch_count - launches1
     e2e_value = world * N_IMAGES * e2e_steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+
     if rank == 0 and isinstance(parity, dict):
         parity["e2e_equals_resident"] = bool((h_out[:64].numpy() == d_out[:64].cpu().numpy()).all())
+
+    # host-link roofline for the e2e number: the same pinned buffers moved both ways at once in 64 MB linear copies on
+    # two streams, no kernel (rank 0, single-GPU run only)
+    link_gbps = None
+    if rank == 0 and world == 1:
+        flat_in, flat_out = h_in.view(-1), h_out.view(-1)
+        dflat_in, dflat_out = d_in.view(-1), d_out.view(-1)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        chunk = 64 << 20
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            s1.wait_event(t0)
+            s2.wait_event(t0)
+            for off in range(0, flat_in.numel(), chunk):
+                with torch.cuda.stream(s1):
+                    dflat_in[off:off + chunk].copy_(flat_in[off:off + chunk], non_blocking=True)
+                with torch.cuda.stream(s2):
+                    flat_out[off:off + chunk].copy_(dflat_out[off:off + chunk], non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s1)
+            torch.cuda.current_stream().wait_stream(s2)
+            t1.record()
+            torch.cuda.synchronize()
+            ms = t0.elapsed_time(t1)
+            best = ms if best is None else min(best, ms)
+        link_gbps = N_IMAGES * IMAGE_BYTES / (best * 1e-3) / 1e9
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -398,6 +427,10 @@ def run_b200_arm(args) -> None:
                     "host_link_GBps_each_way": N_IMAGES * IMAGE_BYTES * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                     "stage_ms_last_step": {"h2d": last.h2d_ms, "kernel": last.kernel_ms, "d2h": last.d2h_ms},
                     "host_affinity": numa,
+                    "link_roofline": None if link_gbps is None else {
+                        "bound": "host link, both directions active (same pinned buffers, 64 MB linear copies, no kernel)",
+                        "peak_GBps_each_way": link_gbps,
+                        "frac": (N_IMAGES * IMAGE_BYTES * e2e_steps / (e2e_ms * 1e-3) / 1e9) / link_gbps},
                     "api": "b200blur_run_host (pinned host buffers, 3 queues, 4-slot device ring, batches fused into ~64 MB transfer chunks)"},
             "gpu_launches": int(resident_launches + e2e_launches),
             "clocks": clocks,
