@@ -17,6 +17,7 @@ from .lib import (  # noqa: F401
     lib_path,
     load,
     partition,
+    plan_row_edge,
     ratio_split_images,
     ratio_split_row,
     version,

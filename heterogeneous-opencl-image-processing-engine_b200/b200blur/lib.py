@@ -77,6 +77,7 @@ _SIGNATURES = {
                                              c_size_t, c_size_t, c_size_t, c_size_t]),
     "b200blur_enqueue_blur": (c_int, [c_void_p, c_int, POINTER(Launch), POINTER(c_int32)]),
     "b200blur_launch_is_vectorised": (c_int, [POINTER(Launch)]),
+    "b200blur_plan_row_edge": (c_int, [c_int, c_int, POINTER(ctypes.c_uint32)]),
     "b200blur_set_kernel_variant": (c_int, [c_void_p, c_int]),
     "b200blur_ctx_launch_count": (c_int64, [c_void_p]),
     "b200blur_partition": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
@@ -168,6 +169,14 @@ def ratio_split_row(height: int, gpu_ratio: float) -> int:
     s = c_int()
     _check(load().b200blur_ratio_split_row(height, gpu_ratio, byref(s)))
     return s.value
+
+
+def plan_row_edge(row_bytes: int, channels: int):
+    """Host-side right-edge plan of the vectorised kernel (b200blur_plan_row_edge) -> dict."""
+    out = (ctypes.c_uint32 * 10)()
+    _check(load().b200blur_plan_row_edge(row_bytes, channels, out))
+    return {"chunks": out[0], "edge_general": bool(out[1]), "edge_prev": bool(out[2]),
+            "sel_last": [out[3 + m] for m in range(6)], "sel_prev": out[9]}
 
 
 def _ptr(p) -> int:

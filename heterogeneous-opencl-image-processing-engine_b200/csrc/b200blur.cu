@@ -808,6 +808,21 @@ int b200blur_launch_rows(b200blur_launch *l, const void *in, void *out, int widt
                                         in_image_stride, out_image_stride, 0, 0);
 }
 
+int b200blur_plan_row_edge(int row_bytes, int channels, uint32_t out[10])
+{
+    if (!out || row_bytes < 1 || channels < 1 || channels > 4 || row_bytes % channels)
+        return fail(B200BLUR_ERR_INVALID, "bad row plan request (row_bytes %d channels %d)", row_bytes, channels);
+    b200blur::StreamParams sp;
+    sp.cpr = (row_bytes + 15) / 16;
+    edge_selectors(sp, row_bytes, channels);
+    out[0] = (uint32_t)sp.cpr;
+    out[1] = (uint32_t)sp.edge_general;
+    out[2] = (uint32_t)sp.edge_prev;
+    for (int m = 0; m < 6; m++) out[3 + m] = sp.sel_last[m];
+    out[9] = sp.sel_prev;
+    return B200BLUR_OK;
+}
+
 int b200blur_launch_is_vectorised(const b200blur_launch *launch)
 {
     if (!launch) return 0;

@@ -179,6 +179,11 @@ B200BLUR_API int b200blur_launch_is_vectorised(const b200blur_launch *launch);
 /* Select the kernel variant of the vectorised path (for profiling/tests): 0 = auto, 1 = register/shuffle
  * stencil, 2 = TMA-bulk staged persistent stencil.  Returns the previous value. */
 B200BLUR_API int b200blur_set_kernel_variant(b200blur_ctx *ctx, int variant);
+/* Host-side plan of the vectorised kernel for rows of `row_bytes` = width*channels bytes (introspection for tests;
+ * needs no GPU): out[0] = live 16-byte chunks per row, out[1] = 1 when the row ends inside a chunk (pitched rows),
+ * out[2] = 1 when the chunk before the last needs its right-neighbour word patched too, out[3..8] = PRMT selectors
+ * for the six window words {wl, w0..w3, wr} of the last chunk, out[9] = selector for the wr word of the chunk before. */
+B200BLUR_API int b200blur_plan_row_edge(int row_bytes, int channels, uint32_t out[10]);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 B200BLUR_API int64_t b200blur_ctx_launch_count(const b200blur_ctx *ctx);
 
