@@ -9,6 +9,7 @@ raises ``BlurError`` if it cannot.
 from .lib import (  # noqa: F401
     BlurError,
     Context,
+    Feed,
     Launch,
     Stats,
     build,

@@ -86,6 +86,15 @@ _SIGNATURES = {
     "b200blur_run_resident": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int,
                                       POINTER(Stats)]),
     "b200blur_run_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, POINTER(Stats)]),
+    "b200blur_feed_create": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "b200blur_feed_destroy": (c_int, [c_void_p]),
+    "b200blur_feed_start": (c_int, [c_void_p]),
+    "b200blur_feed_submit": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(c_int64)]),
+    "b200blur_feed_flush": (c_int, [c_void_p]),
+    "b200blur_feed_wait": (c_int, [c_void_p, c_int64]),
+    "b200blur_feed_completed": (c_int, [c_void_p, c_int64, POINTER(c_int)]),
+    "b200blur_feed_stop": (c_int, [c_void_p]),
+    "b200blur_feed_submitted": (c_int64, [c_void_p]),
     "b200blur_peer_enable": (c_int, [c_void_p, c_void_p]),
     "b200blur_ipc_export": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b200blur_ipc_open": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
@@ -348,6 +357,10 @@ class Context:
                                            batch_size, byref(st) if stats else None))
         return st
 
+    def feed(self, width, height, channels, max_batch_images, capacity=0) -> "Feed":
+        """The batch loop as a resident kernel fed with per-batch descriptors (b200blur_feed_*)."""
+        return Feed(self, width, height, channels, max_batch_images, capacity)
+
     # -- multi-GPU
     def peer_enable(self, other: "Context") -> None:
         _check(self._lib.b200blur_peer_enable(self._h, other._h))
@@ -387,3 +400,58 @@ class Context:
             self.dev_free(d_in)
             self.dev_free(d_out)
         return out
+
+
+class Feed:
+    """b200blur_feed: one persistent kernel per GPU that pulls per-batch descriptors from a ring the host appends to
+    (the reference's batch loop, heterogeneous_blur.c:418-539, without a kernel launch per batch)."""
+
+    def __init__(self, ctx: Context, width, height, channels, max_batch_images, capacity=0):
+        self._lib = load()
+        self._ctx = ctx     # keeps the context alive
+        h = c_void_p()
+        _check(self._lib.b200blur_feed_create(ctx.handle, width, height, channels, max_batch_images, capacity, byref(h)))
+        self._h = h
+
+    def start(self) -> None:
+        _check(self._lib.b200blur_feed_start(self._h))
+
+    def submit(self, d_in, d_out, n_images) -> int:
+        t = c_int64(-1)
+        _check(self._lib.b200blur_feed_submit(self._h, _ptr(d_in), _ptr(d_out), n_images, byref(t)))
+        return t.value
+
+    def flush(self) -> None:
+        _check(self._lib.b200blur_feed_flush(self._h))
+
+    def wait(self, ticket: int) -> None:
+        _check(self._lib.b200blur_feed_wait(self._h, ticket))
+
+    def completed(self, ticket: int) -> bool:
+        d = c_int(0)
+        _check(self._lib.b200blur_feed_completed(self._h, ticket, byref(d)))
+        return bool(d.value)
+
+    def stop(self) -> None:
+        _check(self._lib.b200blur_feed_stop(self._h))
+
+    @property
+    def submitted(self) -> int:
+        return int(self._lib.b200blur_feed_submitted(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.b200blur_feed_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -8,11 +8,13 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -49,8 +51,13 @@ int fail(int code, const char *fmt, ...)
 
 struct EventSlot {
     cudaEvent_t start = nullptr, end = nullptr;
-    bool in_use = false;
+    std::atomic<bool> in_use{false};
 };
+
+// Capacity of a context's event pool.  The pool is ONE fixed array allocated with the context and slots are only ever
+// appended (n_events grows, nothing moves), because b200blur_enqueue_wait_peer lets ANOTHER context's host thread read
+// a slot while its owner is creating new ones: a growing std::vector would reallocate under that reader.
+constexpr int kMaxEvents = 1 << 15;
 
 }  // namespace
 
@@ -58,12 +65,16 @@ struct b200blur_ctx {
     int device = -1;
     int sm_count = 0;
     std::vector<cudaStream_t> queues;
-    std::vector<EventSlot> events;
-    std::vector<int> free_events;
+    std::unique_ptr<EventSlot[]> events;   // kMaxEvents slots, fixed storage (see kMaxEvents)
+    std::atomic<int> n_events{0};          // slots created so far; published with release after the slot is complete
+    std::vector<int> free_events;          // owner thread only
     int kernel_variant = 0;   // 0 auto, 1 register/shuffle strips, 2 TMA-bulk streamed
     int64_t launches = 0;
     // tuning knobs of the streamed kernel (0 = automatic); set from B200BLUR_V2_* at context creation
     int v2_threads = 0, v2_seg = 0, v2_cfg = 0, v2_ctas_per_sm = 0;
+    int tail_div = 4;          // guided tail: last groups are this many times finer (B200BLUR_TAIL_DIV, 1 = off)
+    double tail_rounds = 2.0;  // ... about this many fine groups per resident CTA (B200BLUR_TAIL_ROUNDS)
+    bool use_pdl = true;       // programmatic dependent launch of the streamed kernel (B200BLUR_NO_PDL disables)
     // ring of device buffers owned by b200blur_run_host
     struct Slot {
         uint8_t *d_in = nullptr, *d_out = nullptr;
@@ -80,14 +91,18 @@ struct b200blur_ctx {
     // scratch pair for re-pitching odd-width resident streams (b200blur_run_resident)
     uint8_t *scratch_in = nullptr, *scratch_out = nullptr;
     size_t scratch_bytes = 0;
+    struct b200blur_feed *resident_feed = nullptr;   // descriptor table of b200blur_run_resident(coalesce = 0)
+    const void *resident_in = nullptr; void *resident_out = nullptr;   // ... and what it currently describes
+    int64_t resident_n = 0, resident_calls = 0;
     cudaEvent_t fork_event = nullptr;          // fork/join of the per-batch launches of b200blur_run_resident
     std::vector<cudaEvent_t> join_events;
     // CUDA graph of the last per-batch launch sequence (launch-bound loop: hundreds of small kernels)
     struct GraphKey {
         const void *in = nullptr; void *out = nullptr;
         int w = 0, h = 0, c = 0, batch = 0; int64_t n = 0;
+        int variant = 0;
         bool operator==(const GraphKey &o) const
-        { return in == o.in && out == o.out && w == o.w && h == o.h && c == o.c && batch == o.batch && n == o.n; }
+        { return in == o.in && out == o.out && w == o.w && h == o.h && c == o.c && batch == o.batch && n == o.n && variant == o.variant; }
     } graph_key;
     int graph_seen = 0;                        // times graph_key was requested without a graph
     cudaGraphExec_t graph_exec = nullptr;
@@ -110,6 +125,11 @@ int queue_check(const b200blur_ctx *ctx, int queue)
     return B200BLUR_OK;
 }
 
+bool event_live(const b200blur_ctx *ctx, b200blur_event ev)
+{
+    return ev >= 0 && ev < ctx->n_events.load(std::memory_order_acquire) && ctx->events[ev].in_use.load(std::memory_order_acquire);
+}
+
 int event_begin(b200blur_ctx *ctx, int queue, b200blur_event *ev, int *slot_out)
 {
     *slot_out = -1;
@@ -119,25 +139,57 @@ int event_begin(b200blur_ctx *ctx, int queue, b200blur_event *ev, int *slot_out)
         idx = ctx->free_events.back();
         ctx->free_events.pop_back();
     } else {
-        EventSlot s;
+        idx = ctx->n_events.load(std::memory_order_relaxed);
+        if (idx >= kMaxEvents) return fail(B200BLUR_ERR_NOMEM, "event pool exhausted (%d live events): release events you no longer need", idx);
+        EventSlot &s = ctx->events[idx];
         CU_TRY(cudaEventCreate(&s.start));
-        CU_TRY(cudaEventCreate(&s.end));
-        ctx->events.push_back(s);
-        idx = (int)ctx->events.size() - 1;
+        cudaError_t e = cudaEventCreate(&s.end);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(s.start);
+            s.start = nullptr;
+            return fail(B200BLUR_ERR_CUDA, "%d - cudaEventCreate: %s", (int)e, cudaGetErrorString(e));
+        }
+        ctx->n_events.store(idx + 1, std::memory_order_release);
     }
-    ctx->events[idx].in_use = true;
-    CU_TRY(cudaEventRecord(ctx->events[idx].start, ctx->queues[queue]));
+    cudaError_t e = cudaEventRecord(ctx->events[idx].start, ctx->queues[queue]);
+    if (e != cudaSuccess) {
+        ctx->free_events.push_back(idx);
+        return fail(B200BLUR_ERR_CUDA, "%d - cudaEventRecord: %s", (int)e, cudaGetErrorString(e));
+    }
+    ctx->events[idx].in_use.store(true, std::memory_order_release);
     *slot_out = idx;
     *ev = idx;
     return B200BLUR_OK;
 }
 
-int event_end(b200blur_ctx *ctx, int queue, int slot)
+// Gives a slot taken by event_begin back when the command it was meant to time could not be enqueued.
+int event_abort(b200blur_ctx *ctx, int slot, b200blur_event *ev, int rc)
+{
+    if (slot >= 0) {
+        ctx->events[slot].in_use.store(false, std::memory_order_release);
+        ctx->free_events.push_back(slot);
+        if (ev) *ev = -1;
+    }
+    return rc;
+}
+
+int event_end(b200blur_ctx *ctx, int queue, int slot, b200blur_event *ev = nullptr)
 {
     if (slot < 0) return B200BLUR_OK;
-    CU_TRY(cudaEventRecord(ctx->events[slot].end, ctx->queues[queue]));
+    cudaError_t e = cudaEventRecord(ctx->events[slot].end, ctx->queues[queue]);
+    if (e != cudaSuccess)
+        return event_abort(ctx, slot, ev, fail(B200BLUR_ERR_CUDA, "%d - cudaEventRecord: %s", (int)e, cudaGetErrorString(e)));
     return B200BLUR_OK;
 }
+
+// CU_TRY for a command enqueued between event_begin and event_end: the event slot goes back to the pool on failure.
+#define CU_TRY_EV(expr, slot_, ev_)                                                                    \
+    do {                                                                                               \
+        cudaError_t e2_ = (expr);                                                                      \
+        if (e2_ != cudaSuccess)                                                                        \
+            return event_abort(ctx, slot_, ev_,                                                        \
+                               fail(B200BLUR_ERR_CUDA, "%d - %s failed: %s", (int)e2_, #expr, cudaGetErrorString(e2_))); \
+    } while (0)
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -223,6 +275,7 @@ struct StreamCfg {
     int rb, ns;
     StreamKernel fn[4];       // by channels-1: rows end on a chunk boundary
     StreamKernel fn_edge[4];  // by channels-1: rows end inside a chunk (pitched rows)
+    StreamKernel fn_feed[4];  // by channels-1: FEED mode (per-batch descriptors; tight rows that end on a chunk boundary)
 };
 
 template <int RB, int NS>
@@ -232,7 +285,9 @@ constexpr StreamCfg make_cfg()
                      {b200blur::blur_stream_kernel<1, RB, NS, false>, b200blur::blur_stream_kernel<2, RB, NS, false>,
                       b200blur::blur_stream_kernel<3, RB, NS, false>, b200blur::blur_stream_kernel<4, RB, NS, false>},
                      {b200blur::blur_stream_kernel<1, RB, NS, true>, b200blur::blur_stream_kernel<2, RB, NS, true>,
-                      b200blur::blur_stream_kernel<3, RB, NS, true>, b200blur::blur_stream_kernel<4, RB, NS, true>}};
+                      b200blur::blur_stream_kernel<3, RB, NS, true>, b200blur::blur_stream_kernel<4, RB, NS, true>},
+                     {b200blur::blur_stream_kernel<1, RB, NS, false, true>, b200blur::blur_stream_kernel<2, RB, NS, false, true>,
+                      b200blur::blur_stream_kernel<3, RB, NS, false, true>, b200blur::blur_stream_kernel<4, RB, NS, false, true>}};
 }
 
 // {rows per slot, slots}; index 0 is the default (B200BLUR_V2_CFG selects another for tuning runs)
@@ -276,31 +331,46 @@ void edge_selectors(b200blur::StreamParams &sp, int row_bytes, int channels)
     }
 }
 
-int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s, int queue)
-{
+// Everything a streamed-kernel launch needs besides the stream: geometry, kernel, block/grid/shared memory.
+struct StreamPlan {
     b200blur::StreamParams sp;
+    StreamKernel fn = nullptr;
+    int block = 0;
+    size_t smem = 0;
+    long long slots = 0;   // resident CTAs on the whole GPU for this kernel/block/smem
+};
+
+// Plans the streamed kernel for band geometry `p` (p.n_images images per launch, or -- feed -- per batch at most).
+int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, StreamPlan &plan)
+{
+    b200blur::StreamParams &sp = plan.sp;
+    memset(&sp, 0, sizeof sp);
     sp.b = p;
     sp.cpr = (p.row_bytes + 15) / 16;   // live chunks per row; bytes past row_bytes up to the pitch are padding
     edge_selectors(sp, p.row_bytes, p.channels);
     const StreamCfg &cfg = kStreamCfgs[(ctx->v2_cfg >= 0 && ctx->v2_cfg < kNumStreamCfgs) ? ctx->v2_cfg : 0];
     int threads;
-    if (p.pitch <= 4096) {
-        // full-width rows: a CTA step covers `ipc` images side by side; pick the block size that wastes fewest lanes
+    if (p.pitch <= 4096 && sp.cpr <= 256) {
+        // whole rows: a CTA step covers `ipc` images side by side; pick the block size that wastes fewest lanes
         sp.cb = sp.cpr;
         sp.ncb = 1;
-        sp.margin = 0;
         const int prefer = ctx->v2_threads > 0 ? ctx->v2_threads : 128;
         int best_t = 0;
         double best_score = -1.0;
         for (int t = 64; t <= 256; t += 32) {
             if (t < sp.cb) continue;
-            const int ipc = t / sp.cb;
+            int ipc = t / sp.cb;
+            if (ipc > p.n_images && p.n_images > 0) ipc = (int)p.n_images;   // never more image lanes than images
             const double eff = (double)(ipc * sp.cb) / t;
             const double score = eff - 0.0005 * (t > prefer ? t - prefer : prefer - t);
             if (score > best_score) { best_score = score; best_t = t; }
         }
         threads = best_t;
         sp.ipc = threads / sp.cb;
+        if (sp.ipc > p.n_images && p.n_images > 0) sp.ipc = (int)p.n_images;
+        // Rows as they lie in memory (RB rows of an image = one bulk copy, padding included) while the padding is small;
+        // heavily padded rows (ROI views, pitch >> width*channels) bring only their live chunks, one copy per row.
+        sp.margin = ((long long)p.pitch - sp.cpr * 16 > sp.cpr * 4) ? 16 : 0;
     } else {
         threads = ctx->v2_threads > 0 ? ctx->v2_threads : 128;
         if (threads > 256) threads = 256;
@@ -309,26 +379,32 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
         sp.margin = 16;
         sp.ipc = 1;
     }
-    sp.sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;   // full-width: rows land exactly as they lie in memory
+    auto smem_for = [&](int ipc) {
+        const int sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;
+        return 16 + (size_t)cfg.ns * ipc * cfg.rb * sstride + 16 + 16 * cfg.ns + sizeof(b200blur::GroupMeta) * cfg.ns +
+               (feed ? 24 * b200blur::kFeedDepth : 0);
+    };
+    while (sp.ipc > 1 && smem_for(sp.ipc) > 200 * 1024) sp.ipc--;   // fewer images side by side rather than no launch
+    sp.sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;   // whole rows land exactly as they lie in memory
     sp.slot_bytes = sp.ipc * cfg.rb * sp.sstride;
-    const size_t smem = 16 + (size_t)cfg.ns * sp.slot_bytes + 16 + 24 * cfg.ns;
-    const int block = threads + 32;  // + the producer warp
-    if (smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", smem);
-    StreamKernel fn = sp.edge_general ? cfg.fn_edge[p.channels - 1] : cfg.fn[p.channels - 1];
+    plan.smem = smem_for(sp.ipc);
+    plan.block = threads + (feed ? 64 : 32);  // + the producer warp (+ the accountant warp of a feed)
+    if (plan.smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", plan.smem);
+    plan.fn = feed ? cfg.fn_feed[p.channels - 1] : sp.edge_general ? cfg.fn_edge[p.channels - 1] : cfg.fn[p.channels - 1];
     int per_sm = 0;
     for (auto &ki : ctx->kernel_info)
-        if (ki.fn == (const void *)fn && ki.block == block && ki.smem == smem) per_sm = ki.per_sm;
+        if (ki.fn == (const void *)plan.fn && ki.block == plan.block && ki.smem == plan.smem) per_sm = ki.per_sm;
     if (per_sm == 0) {
         // opt in to the largest dynamic shared-memory size once per kernel (any later, smaller request is covered)
-        CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
+        CU_TRY(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.block, plan.smem));
         if (per_sm < 1) return fail(B200BLUR_ERR_CUDA, "streamed kernel does not fit on an SM");
-        ctx->kernel_info.push_back({(const void *)fn, block, smem, per_sm});
+        ctx->kernel_info.push_back({(const void *)plan.fn, plan.block, plan.smem, per_sm});
     }
     if (ctx->v2_ctas_per_sm > 0 && per_sm > ctx->v2_ctas_per_sm) per_sm = ctx->v2_ctas_per_sm;
-    const long long slots = (long long)ctx->sm_count * per_sm;
+    plan.slots = (long long)ctx->sm_count * per_sm;
     sp.img_blocks = (p.n_images + sp.ipc - 1) / sp.ipc;
-    // Work unit = `seg` output rows of `ipc` images (or of one column block): ~48 KB in + 48 KB out for full-width
+    // Work unit = `seg` output rows of `ipc` images (or of one column block): ~48 KB in + 48 KB out for whole
     // rows, ~128 KB for column blocks; the band is cut into equal segments of about that size.
     int seg;
     if (ctx->v2_seg > 0) {
@@ -340,20 +416,70 @@ int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t
         if (want < 6) want = 6;
         // very small launches only: shorter units until there is one per SM.  (Shrinking further to "fill" every CTA
         // slot makes small launches slower: 143 launches of 35 images take 0.85 ms with 6-row units, 0.44 ms with 24.)
-        while (want > 6 && sp.img_blocks * sp.ncb * ((p.rows + want - 1) / want) < ctx->sm_count) want = (want + 1) / 2;
+        if (!feed)
+            while (want > 6 && sp.img_blocks * sp.ncb * ((p.rows + want - 1) / want) < ctx->sm_count) want = (want + 1) / 2;
         const long long nseg = (p.rows + want - 1) / want;
         seg = (int)((p.rows + nseg - 1) / nseg);
     }
     if (seg > p.rows) seg = p.rows;
     sp.seg = seg;
     sp.nseg = (p.rows + seg - 1) / seg;
-    sp.n_groups = sp.img_blocks * sp.nseg * sp.ncb;
-    if (sp.n_groups >= 0x7fffffffLL || (long long)sp.nseg * sp.ncb >= 0x7fffffffLL)
+    // Guided tail: the image blocks handed out last are cut `tail_div` times finer, about `tail_rounds` groups per
+    // resident CTA of them, so the CTAs finish within a fraction of a coarse group of each other.  (Launches shorter
+    // than a few rounds of coarse groups are all tail, e.g. a 32-row band of 5000 images on one of 8 GPUs.)
+    sp.ib_coarse = sp.img_blocks;
+    sp.seg_fine = seg;
+    sp.nseg_fine = sp.nseg;
+    if (!feed && ctx->tail_div > 1 && ctx->v2_seg <= 0 && sp.img_blocks * sp.nseg * sp.ncb >= 4 * plan.slots) {
+        int seg_fine = (seg + ctx->tail_div - 1) / ctx->tail_div;
+        if (seg_fine < 6) seg_fine = seg < 6 ? seg : 6;
+        if (seg_fine < seg) {
+            const long long nseg_fine = (p.rows + seg_fine - 1) / seg_fine;
+            seg_fine = (int)((p.rows + nseg_fine - 1) / nseg_fine);
+            const long long per_block_fine = nseg_fine * sp.ncb;
+            long long ib_fine = (long long)(ctx->tail_rounds * (double)plan.slots / (double)per_block_fine + 0.999);
+            if (ib_fine > sp.img_blocks) ib_fine = sp.img_blocks;
+            if (ib_fine > 0) {
+                sp.ib_coarse = sp.img_blocks - ib_fine;
+                sp.seg_fine = seg_fine;
+                sp.nseg_fine = (int)((p.rows + seg_fine - 1) / seg_fine);
+            }
+        }
+    }
+    sp.g_coarse = sp.ib_coarse * sp.nseg * sp.ncb;
+    sp.n_groups = sp.g_coarse + (sp.img_blocks - sp.ib_coarse) * sp.nseg_fine * sp.ncb;
+    if (sp.n_groups >= 0x7fffffffLL || (long long)sp.nseg * sp.ncb >= 0x7fffffffLL || (long long)sp.nseg_fine * sp.ncb >= 0x7fffffffLL)
         return fail(B200BLUR_ERR_INVALID, "too many work units for one launch (%lld)", sp.n_groups);
-    sp.work = ctx->d_work + 2 * queue;
-    const long long grid = sp.n_groups < slots ? sp.n_groups : slots;
-    fn<<<(unsigned)grid, block, smem, s>>>(sp);
     return B200BLUR_OK;
+}
+
+// Launches a planned streamed kernel with programmatic stream serialisation: when the previous command in the stream
+// is also one of these kernels, this one's prologue (CTA launch, barrier init) overlaps that one's tail; the kernel's
+// griddepcontrol.wait keeps every global access after the previous kernel's completion.
+int launch_planned(b200blur_ctx *ctx, const StreamPlan &plan, long long grid, cudaStream_t s)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)plan.block);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+    CU_TRY(cudaLaunchKernelEx(&cfg, plan.fn, plan.sp));
+    return B200BLUR_OK;
+}
+
+int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s, int queue)
+{
+    StreamPlan plan;
+    if (int rc = plan_stream(ctx, p, false, plan)) return rc;
+    plan.sp.work = ctx->d_work + 2 * queue;
+    const long long grid = plan.sp.n_groups < plan.slots ? plan.sp.n_groups : plan.slots;
+    return launch_planned(ctx, plan, grid, s);
 }
 
 // Launches the device code for one b200blur_launch on stream s.  Returns the number of kernels launched.
@@ -430,6 +556,157 @@ double now_ms()
 
 }  // namespace
 
+// A feed: the persistent form of the batch loop.  See include/b200blur.h (b200blur_feed_*) and StreamParams.
+struct b200blur_feed {
+    b200blur_ctx *ctx = nullptr;
+    int width = 0, height = 0, channels = 0, max_batch = 0, cap = 0;
+    size_t image_bytes = 0;
+    StreamPlan plan;
+    b200blur::FeedBatch *d_batches = nullptr, *h_batches = nullptr;   // device ring and its pinned host mirror
+    unsigned long long *d_ctl = nullptr;     // [0] tail, [1] closed, [2] watchdog, [3] unused; [4],[5] work counters
+    unsigned int *d_count = nullptr;         // per slot: consumer-warp arrivals of the batch in it
+    unsigned int *h_done = nullptr;          // cap + 1 words, host-mapped: per slot completion, [cap] = watchdog tripped
+    unsigned long long *h_ctl = nullptr;     // pinned ring of control words (sources of the small async copies)
+    int h_ctl_pos = 0;
+    cudaStream_t kstream = nullptr, cstream = nullptr;
+    int64_t submitted = 0, flushed = 0, base = 0;
+    bool running = false, failed = false;
+    unsigned long long timeout_ns = 5000000000ull;
+};
+
+namespace {
+constexpr int kFeedCtlRing = 256;
+
+void feed_release(b200blur_feed *f)
+{
+    if (!f) return;
+    if (f->d_batches) cudaFree(f->d_batches);
+    if (f->d_ctl) cudaFree(f->d_ctl);
+    if (f->d_count) cudaFree(f->d_count);
+    if (f->h_batches) cudaFreeHost(f->h_batches);
+    if (f->h_done) cudaFreeHost(f->h_done);
+    if (f->h_ctl) cudaFreeHost(f->h_ctl);
+    if (f->kstream) cudaStreamDestroy(f->kstream);
+    if (f->cstream) cudaStreamDestroy(f->cstream);
+    delete f;
+}
+
+// Can the feed kernel run this geometry?  (tight rows ending on a 16-byte boundary, wide enough for bulk copies)
+bool feed_eligible(int width, int height, int channels)
+{
+    const size_t row_bytes = (size_t)width * channels;
+    return channels >= 1 && channels <= 4 && height >= 1 && row_bytes >= 256 && row_bytes % 16 == 0 && row_bytes <= 0x7fffffffULL;
+}
+
+int feed_build(b200blur_ctx *ctx, int width, int height, int channels, int max_batch, int cap, bool own_streams, b200blur_feed **out)
+{
+    *out = nullptr;
+    if (!feed_eligible(width, height, channels))
+        return fail(B200BLUR_ERR_INVALID, "feed needs channels <= 4 and rows of width*channels >= 256 bytes, a multiple of 16 (got %dx%dx%d)",
+                    width, height, channels);
+    if (max_batch < 1 || cap < 2) return fail(B200BLUR_ERR_INVALID, "feed needs max_batch >= 1 and capacity >= 2");
+    CU_TRY(cudaSetDevice(ctx->device));
+    b200blur_feed *f = new (std::nothrow) b200blur_feed;
+    if (!f) return fail(B200BLUR_ERR_NOMEM, "out of host memory");
+    f->ctx = ctx;
+    f->width = width; f->height = height; f->channels = channels; f->max_batch = max_batch; f->cap = cap;
+    f->image_bytes = (size_t)width * height * channels;
+    if (const char *v = getenv("B200BLUR_FEED_TIMEOUT_MS")) f->timeout_ns = (unsigned long long)atoll(v) * 1000000ull;
+    b200blur::BandParams p;
+    memset(&p, 0, sizeof p);
+    p.in_stride = p.out_stride = f->image_bytes;
+    p.row_bytes = p.pitch = p.out_pitch = width * channels;
+    p.rows = height;
+    p.width = width;
+    p.channels = channels;
+    p.n_images = max_batch;
+    int rc = plan_stream(ctx, p, true, f->plan);
+    auto bail = [&](int code) { feed_release(f); return code; };
+    if (rc) return bail(rc);
+    b200blur::StreamParams &sp = f->plan.sp;
+    const long long gpb = sp.img_blocks * sp.nseg * sp.ncb;
+    if (gpb >= (1LL << 24)) return bail(fail(B200BLUR_ERR_INVALID, "batch too large for a feed (%lld groups)", gpb));
+#define FEED_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return bail(fail(e_ == cudaErrorMemoryAllocation ? B200BLUR_ERR_NOMEM : B200BLUR_ERR_CUDA, "%d - %s failed: %s", (int)e_, #expr, cudaGetErrorString(e_))); } while (0)
+    FEED_TRY(cudaMalloc((void **)&f->d_batches, sizeof(b200blur::FeedBatch) * cap));
+    FEED_TRY(cudaMalloc((void **)&f->d_ctl, 8 * 8));
+    FEED_TRY(cudaMemset(f->d_ctl, 0, 8 * 8));
+    FEED_TRY(cudaMalloc((void **)&f->d_count, sizeof(unsigned int) * cap));
+    FEED_TRY(cudaMemset(f->d_count, 0, sizeof(unsigned int) * cap));
+    FEED_TRY(cudaHostAlloc((void **)&f->h_batches, sizeof(b200blur::FeedBatch) * cap, cudaHostAllocPortable));
+    FEED_TRY(cudaHostAlloc((void **)&f->h_done, sizeof(unsigned int) * (cap + 1), cudaHostAllocPortable | cudaHostAllocMapped));
+    memset(f->h_done, 0, sizeof(unsigned int) * (cap + 1));
+    FEED_TRY(cudaHostAlloc((void **)&f->h_ctl, 8 * kFeedCtlRing, cudaHostAllocPortable));
+    if (own_streams) {
+        FEED_TRY(cudaStreamCreateWithFlags(&f->kstream, cudaStreamNonBlocking));
+        FEED_TRY(cudaStreamCreateWithFlags(&f->cstream, cudaStreamNonBlocking));
+    }
+    void *d_done = nullptr;
+    FEED_TRY(cudaHostGetDevicePointer(&d_done, f->h_done, 0));
+    FEED_TRY(cudaDeviceSynchronize());   // the memsets above are on the legacy stream
+#undef FEED_TRY
+    sp.batches = f->d_batches;
+    sp.feed_ctl = f->d_ctl;
+    sp.work = f->d_ctl + 4;
+    sp.feed_count = f->d_count;
+    sp.feed_done = static_cast<volatile unsigned int *>(d_done);
+    sp.feed_cap = cap;
+    sp.feed_gpb = (int)gpb;
+    sp.feed_target = (unsigned int)gpb * (unsigned int)(f->plan.block / 32 - 2);   // consumer warps per CTA
+    sp.feed_timeout_ns = f->timeout_ns;
+    *out = f;
+    return B200BLUR_OK;
+}
+
+// next pinned control word holding `value` (the source of a small async copy must stay untouched until the copy runs)
+int feed_ctl_word(b200blur_feed *f, cudaStream_t s, unsigned long long value, unsigned long long **word)
+{
+    if (f->h_ctl_pos == kFeedCtlRing) {
+        CU_TRY(cudaStreamSynchronize(s));
+        f->h_ctl_pos = 0;
+    }
+    f->h_ctl[f->h_ctl_pos] = value;
+    *word = f->h_ctl + f->h_ctl_pos++;
+    return B200BLUR_OK;
+}
+
+// publishes descriptors [flushed, submitted) and the new tail on stream s
+int feed_publish(b200blur_feed *f, cudaStream_t s)
+{
+    if (f->flushed == f->submitted) return B200BLUR_OK;
+    int64_t i = f->flushed;
+    while (i < f->submitted) {
+        const int slot = (int)(i % f->cap);
+        int64_t n = f->submitted - i;
+        if (n > f->cap - slot) n = f->cap - slot;
+        CU_TRY(cudaMemcpyAsync(f->d_batches + slot, f->h_batches + slot, sizeof(b200blur::FeedBatch) * (size_t)n, cudaMemcpyHostToDevice, s));
+        i += n;
+    }
+    unsigned long long *w;
+    if (int rc = feed_ctl_word(f, s, (unsigned long long)(f->submitted - f->base), &w)) return rc;
+    CU_TRY(cudaMemcpyAsync(f->d_ctl, w, 8, cudaMemcpyHostToDevice, s));
+    f->flushed = f->submitted;
+    return B200BLUR_OK;
+}
+
+bool feed_slot_done(const b200blur_feed *f, int64_t ticket)
+{
+    const unsigned int seen = *(volatile unsigned int *)(f->h_done + ticket % f->cap);
+    return (int)(seen - (unsigned int)(ticket + 1)) >= 0 && seen != 0;
+}
+
+int feed_launch(b200blur_feed *f, cudaStream_t s, long long total_groups_or_0)
+{
+    b200blur_ctx *ctx = f->ctx;
+    f->plan.sp.feed_base = (unsigned long long)f->base;
+    long long grid = f->plan.slots;
+    if (total_groups_or_0 > 0 && total_groups_or_0 < grid) grid = total_groups_or_0;
+    if (int rc = launch_planned(ctx, f->plan, grid, s)) return rc;
+    ctx->launches++;
+    return B200BLUR_OK;
+}
+
+}  // namespace
+
 // ============================================================================================== C ABI
 extern "C" {
 
@@ -483,6 +760,11 @@ int b200blur_ctx_create(int device, int n_queues, b200blur_ctx **out)
     b200blur_ctx *ctx = new (std::nothrow) b200blur_ctx;
     if (!ctx) return fail(B200BLUR_ERR_NOMEM, "out of host memory");
     ctx->device = device;
+    ctx->events.reset(new (std::nothrow) EventSlot[kMaxEvents]);
+    if (!ctx->events) {
+        delete ctx;
+        return fail(B200BLUR_ERR_NOMEM, "out of host memory");
+    }
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) {
@@ -496,6 +778,9 @@ int b200blur_ctx_create(int device, int n_queues, b200blur_ctx **out)
     ctx->v2_seg = env_int("B200BLUR_V2_SEG");
     ctx->v2_cfg = env_int("B200BLUR_V2_CFG");
     ctx->v2_ctas_per_sm = env_int("B200BLUR_V2_CTAS");
+    if (getenv("B200BLUR_TAIL_DIV")) ctx->tail_div = env_int("B200BLUR_TAIL_DIV");
+    if (getenv("B200BLUR_TAIL_ROUNDS")) ctx->tail_rounds = atof(getenv("B200BLUR_TAIL_ROUNDS"));
+    ctx->use_pdl = getenv("B200BLUR_NO_PDL") == nullptr;
     for (int i = 0; i < n_queues; i++) {
         cudaStream_t s;
         e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
@@ -538,6 +823,7 @@ int b200blur_ctx_destroy(b200blur_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (auto q : ctx->queues) cudaStreamSynchronize(q);
     ring_release(ctx);
+    if (ctx->resident_feed) feed_release(ctx->resident_feed);
     if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->scratch_in) cudaFree(ctx->scratch_in);
     if (ctx->scratch_out) cudaFree(ctx->scratch_out);
@@ -545,9 +831,9 @@ int b200blur_ctx_destroy(b200blur_ctx *ctx)
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     for (auto e : ctx->join_events)
         if (e) cudaEventDestroy(e);
-    for (auto &e : ctx->events) {
-        if (e.start) cudaEventDestroy(e.start);
-        if (e.end) cudaEventDestroy(e.end);
+    for (int i = 0, n = ctx->n_events.load(); i < n; i++) {
+        if (ctx->events[i].start) cudaEventDestroy(ctx->events[i].start);
+        if (ctx->events[i].end) cudaEventDestroy(ctx->events[i].end);
     }
     for (auto q : ctx->queues) cudaStreamDestroy(q);
     delete ctx;
@@ -627,7 +913,7 @@ int b200blur_event_ms(b200blur_ctx *ctx, b200blur_event ev, double *ms)
 {
     if (int rc = ctx_check(ctx)) return rc;
     if (!ms) return fail(B200BLUR_ERR_INVALID, "ms is NULL");
-    if (ev < 0 || ev >= (int)ctx->events.size() || !ctx->events[ev].in_use)
+    if (!event_live(ctx, ev))
         return fail(B200BLUR_ERR_INVALID, "event %d is not live", (int)ev);
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaEventSynchronize(ctx->events[ev].end));
@@ -640,9 +926,9 @@ int b200blur_event_ms(b200blur_ctx *ctx, b200blur_event ev, double *ms)
 int b200blur_event_release(b200blur_ctx *ctx, b200blur_event ev)
 {
     if (int rc = ctx_check(ctx)) return rc;
-    if (ev < 0 || ev >= (int)ctx->events.size() || !ctx->events[ev].in_use)
+    if (!event_live(ctx, ev))
         return fail(B200BLUR_ERR_INVALID, "event %d is not live", (int)ev);
-    ctx->events[ev].in_use = false;
+    ctx->events[ev].in_use.store(false, std::memory_order_release);
     ctx->free_events.push_back(ev);
     return B200BLUR_OK;
 }
@@ -654,7 +940,7 @@ int b200blur_enqueue_marker(b200blur_ctx *ctx, int queue, b200blur_event *ev)
     CU_TRY(cudaSetDevice(ctx->device));
     int slot;
     if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
-    return event_end(ctx, queue, slot);
+    return event_end(ctx, queue, slot, ev);
 }
 
 int b200blur_events_elapsed_ms(b200blur_ctx *ctx, b200blur_event from, b200blur_event to, double *ms)
@@ -662,7 +948,7 @@ int b200blur_events_elapsed_ms(b200blur_ctx *ctx, b200blur_event from, b200blur_
     if (int rc = ctx_check(ctx)) return rc;
     if (!ms) return fail(B200BLUR_ERR_INVALID, "ms is NULL");
     for (b200blur_event ev : {from, to})
-        if (ev < 0 || ev >= (int)ctx->events.size() || !ctx->events[ev].in_use)
+        if (!event_live(ctx, ev))
             return fail(B200BLUR_ERR_INVALID, "event %d is not live", (int)ev);
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaEventSynchronize(ctx->events[from].end));
@@ -676,7 +962,7 @@ int b200blur_events_elapsed_ms(b200blur_ctx *ctx, b200blur_event from, b200blur_
 int b200blur_enqueue_wait(b200blur_ctx *ctx, int queue, b200blur_event ev)
 {
     if (int rc = queue_check(ctx, queue)) return rc;
-    if (ev < 0 || ev >= (int)ctx->events.size() || !ctx->events[ev].in_use)
+    if (!event_live(ctx, ev))
         return fail(B200BLUR_ERR_INVALID, "event %d is not live", (int)ev);
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaStreamWaitEvent(ctx->queues[queue], ctx->events[ev].end, 0));
@@ -687,7 +973,7 @@ int b200blur_enqueue_wait_peer(b200blur_ctx *ctx, int queue, b200blur_ctx *src, 
 {
     if (int rc = queue_check(ctx, queue)) return rc;
     if (int rc = ctx_check(src)) return rc;
-    if (ev < 0 || ev >= (int)src->events.size() || !src->events[ev].in_use)
+    if (!event_live(src, ev))
         return fail(B200BLUR_ERR_INVALID, "event %d is not live in the source context", (int)ev);
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaStreamWaitEvent(ctx->queues[queue], src->events[ev].end, 0));
@@ -703,8 +989,8 @@ int b200blur_enqueue_write(b200blur_ctx *ctx, int queue, void *dst_dev, const vo
     CU_TRY(cudaSetDevice(ctx->device));
     int slot;
     if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
-    if (bytes) CU_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->queues[queue]));
-    return event_end(ctx, queue, slot);
+    if (bytes) CU_TRY_EV(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->queues[queue]), slot, ev);
+    return event_end(ctx, queue, slot, ev);
 }
 
 int b200blur_enqueue_read(b200blur_ctx *ctx, int queue, void *dst_host, const void *src_dev, size_t bytes,
@@ -715,8 +1001,8 @@ int b200blur_enqueue_read(b200blur_ctx *ctx, int queue, void *dst_host, const vo
     CU_TRY(cudaSetDevice(ctx->device));
     int slot;
     if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
-    if (bytes) CU_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->queues[queue]));
-    return event_end(ctx, queue, slot);
+    if (bytes) CU_TRY_EV(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->queues[queue]), slot, ev);
+    return event_end(ctx, queue, slot, ev);
 }
 
 int b200blur_enqueue_write_2d(b200blur_ctx *ctx, int queue, void *dst_dev, size_t dst_pitch, const void *src_host,
@@ -728,9 +1014,9 @@ int b200blur_enqueue_write_2d(b200blur_ctx *ctx, int queue, void *dst_dev, size_
     int slot;
     if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
     if (row_bytes && rows)
-        CU_TRY(cudaMemcpy2DAsync(dst_dev, dst_pitch, src_host, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice,
-                                 ctx->queues[queue]));
-    return event_end(ctx, queue, slot);
+        CU_TRY_EV(cudaMemcpy2DAsync(dst_dev, dst_pitch, src_host, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice,
+                                    ctx->queues[queue]), slot, ev);
+    return event_end(ctx, queue, slot, ev);
 }
 
 int b200blur_enqueue_read_2d(b200blur_ctx *ctx, int queue, void *dst_host, size_t dst_pitch, const void *src_dev,
@@ -742,9 +1028,9 @@ int b200blur_enqueue_read_2d(b200blur_ctx *ctx, int queue, void *dst_host, size_
     int slot;
     if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
     if (row_bytes && rows)
-        CU_TRY(cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost,
-                                 ctx->queues[queue]));
-    return event_end(ctx, queue, slot);
+        CU_TRY_EV(cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost,
+                                    ctx->queues[queue]), slot, ev);
+    return event_end(ctx, queue, slot, ev);
 }
 
 int b200blur_finish(b200blur_ctx *ctx, int queue)
@@ -837,8 +1123,8 @@ int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200blur_launch *l
     int slot;
     if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
     int nk;
-    if (int rc = do_launch(ctx, queue, launch, &nk)) return rc;
-    return event_end(ctx, queue, slot);
+    if (int rc = do_launch(ctx, queue, launch, &nk)) return event_abort(ctx, slot, ev, rc);
+    return event_end(ctx, queue, slot, ev);
 }
 
 // ----------------------------------------------------------------------------------- work distribution (L4)
@@ -880,6 +1166,144 @@ int b200blur_ratio_split_row(int height, float gpu_ratio, int *split_row)
     *split_row = s;
     return B200BLUR_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------ feed (L3)
+int b200blur_feed_create(b200blur_ctx *ctx, int width, int height, int channels, int max_batch_images, int capacity,
+                         b200blur_feed **feed)
+{
+    if (int rc = ctx_check(ctx)) return rc;
+    if (!feed) return fail(B200BLUR_ERR_INVALID, "feed out-pointer is NULL");
+    if (capacity <= 0) capacity = 4096;
+    return feed_build(ctx, width, height, channels, max_batch_images, capacity, true, feed);
+}
+
+int b200blur_feed_start(b200blur_feed *f)
+{
+    if (!f) return fail(B200BLUR_ERR_INVALID, "feed is NULL");
+    if (f->failed) return fail(B200BLUR_ERR_CUDA, "feed is in a failed state (watchdog tripped); destroy it");
+    if (f->running) return fail(B200BLUR_ERR_INVALID, "feed is already running");
+    CU_TRY(cudaSetDevice(f->ctx->device));
+    // batches submitted before start are part of this run: the kernel numbers batches from `base`
+    f->base = f->flushed;
+    unsigned long long *w;
+    if (int rc = feed_ctl_word(f, f->kstream, 0ull, &w)) return rc;
+    CU_TRY(cudaMemcpyAsync(f->d_ctl, w, 8, cudaMemcpyHostToDevice, f->kstream));       // tail = 0
+    CU_TRY(cudaMemcpyAsync(f->d_ctl + 1, w, 8, cudaMemcpyHostToDevice, f->kstream));   // closed = 0
+    CU_TRY(cudaStreamSynchronize(f->kstream));
+    if (int rc = feed_launch(f, f->kstream, 0)) return rc;
+    f->running = true;
+    return B200BLUR_OK;
+}
+
+int b200blur_feed_submit(b200blur_feed *f, const void *d_in, void *d_out, int n_images, int64_t *ticket)
+{
+    if (!f) return fail(B200BLUR_ERR_INVALID, "feed is NULL");
+    if (f->failed) return fail(B200BLUR_ERR_CUDA, "feed is in a failed state (watchdog tripped); destroy it");
+    if (n_images < 1 || n_images > f->max_batch)
+        return fail(B200BLUR_ERR_INVALID, "batch of %d images (feed takes 1..%d)", n_images, f->max_batch);
+    if (!d_in || !d_out || !aligned16(d_in) || !aligned16(d_out) || d_in == d_out)
+        return fail(B200BLUR_ERR_INVALID, "feed batches need distinct, 16-byte aligned device pointers");
+    const int64_t t = f->submitted;
+    if (t >= f->cap) {
+        // the descriptor slot is free once the batch that used it last has completed
+        if (!feed_slot_done(f, t - f->cap)) {
+            if (!f->running) return fail(B200BLUR_ERR_INVALID, "feed ring is full (%d batches) and the feed is not running", f->cap);
+            if (int rc = b200blur_feed_wait(f, t - f->cap)) return rc;
+        }
+    }
+    b200blur::FeedBatch &b = f->h_batches[t % f->cap];
+    memset(&b, 0, sizeof b);
+    b.in = static_cast<const uint8_t *>(d_in);
+    b.out = static_cast<uint8_t *>(d_out);
+    b.n_images = n_images;
+    f->submitted = t + 1;
+    if (ticket) *ticket = t;
+    return B200BLUR_OK;
+}
+
+int b200blur_feed_flush(b200blur_feed *f)
+{
+    if (!f) return fail(B200BLUR_ERR_INVALID, "feed is NULL");
+    if (!f->running) return fail(B200BLUR_ERR_INVALID, "feed is not running (b200blur_feed_start first)");
+    CU_TRY(cudaSetDevice(f->ctx->device));
+    return feed_publish(f, f->cstream);
+}
+
+int b200blur_feed_completed(b200blur_feed *f, int64_t ticket, int *done)
+{
+    if (!f || !done) return fail(B200BLUR_ERR_INVALID, "NULL pointer in feed_completed");
+    if (ticket < 0 || ticket >= f->submitted) return fail(B200BLUR_ERR_INVALID, "ticket %lld was never issued", (long long)ticket);
+    *done = feed_slot_done(f, ticket) ? 1 : 0;
+    return B200BLUR_OK;
+}
+
+int b200blur_feed_wait(b200blur_feed *f, int64_t ticket)
+{
+    if (!f) return fail(B200BLUR_ERR_INVALID, "feed is NULL");
+    if (ticket < 0 || ticket >= f->submitted) return fail(B200BLUR_ERR_INVALID, "ticket %lld was never issued", (long long)ticket);
+    if (feed_slot_done(f, ticket)) return B200BLUR_OK;
+    if (!f->running) return fail(B200BLUR_ERR_INVALID, "feed is not running: batch %lld cannot complete", (long long)ticket);
+    if (ticket >= f->flushed)
+        if (int rc = b200blur_feed_flush(f)) return rc;
+    const double t0 = now_ms();
+    const double limit_ms = (double)f->timeout_ns / 1e6 + 2000.0;
+    for (unsigned spin = 0;; spin++) {
+        if (feed_slot_done(f, ticket)) return B200BLUR_OK;
+        if (*(volatile unsigned int *)(f->h_done + f->cap)) {
+            f->failed = true;
+            return fail(B200BLUR_ERR_CUDA, "feed watchdog tripped: the kernel waited too long for the host and stopped");
+        }
+        if ((spin & 1023) == 1023) {
+            if (cudaStreamQuery(f->kstream) != cudaErrorNotReady) {   // kernel gone (error or stopped) without completing it
+                if (feed_slot_done(f, ticket)) return B200BLUR_OK;
+                f->failed = true;
+                cudaError_t e = cudaGetLastError();
+                return fail(B200BLUR_ERR_CUDA, "feed kernel ended before batch %lld completed (%s)", (long long)ticket, cudaGetErrorString(e));
+            }
+            if (now_ms() - t0 > limit_ms) {
+                f->failed = true;
+                return fail(B200BLUR_ERR_CUDA, "timed out waiting for batch %lld", (long long)ticket);
+            }
+        }
+    }
+}
+
+int b200blur_feed_stop(b200blur_feed *f)
+{
+    if (!f) return fail(B200BLUR_ERR_INVALID, "feed is NULL");
+    if (!f->running) return B200BLUR_OK;
+    CU_TRY(cudaSetDevice(f->ctx->device));
+    int rc = feed_publish(f, f->cstream);
+    unsigned long long *w;
+    if (!rc) rc = feed_ctl_word(f, f->cstream, 1ull, &w);
+    if (!rc) {
+        CU_TRY(cudaMemcpyAsync(f->d_ctl + 1, w, 8, cudaMemcpyHostToDevice, f->cstream));   // closed = 1 (after the final tail)
+        CU_TRY(cudaStreamSynchronize(f->cstream));
+    }
+    cudaError_t e = cudaStreamSynchronize(f->kstream);   // the kernel drains what was published and exits
+    f->running = false;
+    if (e != cudaSuccess) {
+        f->failed = true;
+        return fail(B200BLUR_ERR_CUDA, "%d - feed kernel: %s", (int)e, cudaGetErrorString(e));
+    }
+    if (*(volatile unsigned int *)(f->h_done + f->cap)) {
+        f->failed = true;
+        return fail(B200BLUR_ERR_CUDA, "feed watchdog tripped: the kernel waited too long for the host and stopped");
+    }
+    return rc;
+}
+
+int b200blur_feed_destroy(b200blur_feed *f)
+{
+    if (!f) return B200BLUR_OK;
+    cudaSetDevice(f->ctx->device);
+    if (f->running) b200blur_feed_stop(f);
+    feed_release(f);
+    return B200BLUR_OK;
+}
+
+int64_t b200blur_feed_submitted(const b200blur_feed *f) { return f ? f->submitted : 0; }
 
 // ------------------------------------------------------------------------------------------- stream engines
 int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int width, int height, int channels,
@@ -958,11 +1382,68 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
         }
         return B200BLUR_OK;
     }
-    const int64_t step = coalesce ? (n_images > 0 ? n_images : 1) : batch_size;
+    // One work descriptor per batch (coalesce == 0): the batches go through the feed kernel as a descriptor table --
+    // one kernel launch per call, groups never span batches, every batch completes on its own (flag in host-mapped
+    // memory).  A repeated identical request re-uses the table that is already on the device: no copies at all.
+    // coalesce == 2 (or B200BLUR_NO_FEED) keeps the round-1 form, one kernel LAUNCH per batch, for comparison.
+    static const bool env_no_feed = getenv("B200BLUR_NO_FEED") != nullptr;
+    const int64_t n_batches = (n_images + batch_size - 1) / batch_size;
+    if (coalesce == 0 && !env_no_feed && n_batches > 1 && n_batches < (1 << 26) && feed_eligible(width, height, channels) &&
+        aligned16(d_in) && aligned16(d_out) && d_in != d_out && ctx->kernel_variant != 1) {
+        b200blur_feed *f = ctx->resident_feed;
+        if (!f || f->width != width || f->height != height || f->channels != channels || f->max_batch != batch_size ||
+            f->cap != n_batches) {   // (table mode: descriptor b lives in ring slot b, so the ring is exactly the table)
+            if (f) {
+                CU_TRY(cudaStreamSynchronize(s));
+                feed_release(f);
+                ctx->resident_feed = nullptr;
+            }
+            if (int rc = feed_build(ctx, width, height, channels, batch_size, (int)(n_batches < 2 ? 2 : n_batches), false, &f))
+                return event_abort(ctx, slot, nullptr, rc);
+            ctx->resident_feed = f;
+            ctx->resident_in = nullptr;
+        }
+        const long long total_groups = (long long)n_batches * f->plan.sp.feed_gpb;
+        if (total_groups < 0x7fffffffLL) {
+            if (ctx->resident_in != d_in || ctx->resident_out != d_out || ctx->resident_n != n_images) {
+                CU_TRY(cudaStreamSynchronize(s));   // the table (and its pinned mirror) may still be in use
+                for (int64_t b = 0; b < n_batches; b++) {
+                    b200blur::FeedBatch &d = f->h_batches[b];
+                    memset(&d, 0, sizeof d);
+                    d.in = static_cast<const uint8_t *>(d_in) + (size_t)b * batch_size * image_bytes;
+                    d.out = static_cast<uint8_t *>(d_out) + (size_t)b * batch_size * image_bytes;
+                    d.n_images = (int)((n_images - b * batch_size < batch_size) ? n_images - b * batch_size : batch_size);
+                }
+                f->h_ctl[0] = (unsigned long long)n_batches;   // tail: everything is published before the kernel starts
+                f->h_ctl[1] = 1ull;                            // closed
+                CU_TRY(cudaMemcpyAsync(f->d_batches, f->h_batches, sizeof(b200blur::FeedBatch) * (size_t)n_batches,
+                                       cudaMemcpyHostToDevice, s));
+                CU_TRY(cudaMemcpyAsync(f->d_ctl, f->h_ctl, 16, cudaMemcpyHostToDevice, s));
+                ctx->resident_in = d_in;
+                ctx->resident_out = d_out;
+                ctx->resident_n = n_images;
+            }
+            f->base = ctx->resident_calls++ * n_batches;
+            if (int rc = feed_launch(f, s, total_groups)) return event_abort(ctx, slot, nullptr, rc);
+            if (stats) {
+                if (int rc = event_end(ctx, 0, slot)) return rc;
+                double ms = 0;
+                if (int rc = b200blur_event_ms(ctx, ev_all, &ms)) return rc;
+                b200blur_event_release(ctx, ev_all);
+                memset(stats, 0, sizeof *stats);
+                stats->kernel_ms = ms;
+                stats->images = n_images;
+                stats->launches = 1;
+                stats->wall_ms = now_ms() - t0;
+            }
+            return B200BLUR_OK;
+        }
+    }
+    const int64_t step = coalesce == 1 ? (n_images > 0 ? n_images : 1) : batch_size;
     // One launch per batch (coalesce == 0): the batches are independent, so their launches are spread round-robin
     // over all queues of the context and overlap each other's ramp-up and tail; queue 0 forks and joins the others,
     // so the call still behaves like one in-order operation on queue 0.
-    const int nq = (!coalesce && n_images > (int64_t)batch_size) ? (int)ctx->queues.size() : 1;
+    const int nq = (coalesce != 1 && n_images > (int64_t)batch_size) ? (int)ctx->queues.size() : 1;
     cudaEvent_t fork = nullptr;
     if (nq > 1) {
         if (!ctx->fork_event) CU_TRY(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
@@ -978,11 +1459,16 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
     static const bool env_no_graph = getenv("B200BLUR_NO_GRAPH") != nullptr;
     b200blur_ctx::GraphKey key;
     key.in = d_in; key.out = d_out; key.w = width; key.h = height; key.c = channels; key.batch = batch_size; key.n = n_images;
+    key.variant = ctx->kernel_variant;
     const bool graphable = nq > 1 && !env_no_graph && (n_images + step - 1) / step >= 8;
     bool capturing = false, replayed = false;
     if (graphable) {
         if (ctx->graph_exec && ctx->graph_key == key) {
             CU_TRY(cudaGraphLaunch(ctx->graph_exec, s));
+            // the graph's kernels used the work counters of queues 1.. too: later launches on those queues must come
+            // after it (the eager path gets this ordering from its join events)
+            CU_TRY(cudaEventRecord(fork, s));
+            for (int q = 1; q < nq; q++) CU_TRY(cudaStreamWaitEvent(ctx->queues[q], fork, 0));
             launches = ctx->graph_launches;
             ctx->launches += launches;
             replayed = true;

@@ -210,7 +210,7 @@ blur_strip_kernel(const BandParams p, int cpr, int n_strips)
 }
 
 // ------------------------------------------------------------------ variant 2: TMA-bulk streamed persistent stencil
-// The Blackwell-native form.  Persistent CTAs (a few per SM) each stream "items" -- a segment of `seg` output rows of
+// The Blackwell-native form.  Persistent CTAs (a few per SM) each stream "groups" -- a segment of `seg` output rows of
 // a column block of `ipc` consecutive images -- through a ring of NS shared-memory slots.  One elected thread feeds
 // the ring with 1-D bulk async copies (cp.async.bulk global->shared, completion on an mbarrier; SASS UBLKCP): because
 // a small frame's rows are contiguous in memory, RB rows of an image arrive as ONE bulk copy; wide frames use one
@@ -220,19 +220,31 @@ blur_strip_kernel(const BandParams p, int cpr, int n_strips)
 // held by the ring (NS-1 slots per CTA), not by registers, and a segment re-reads only 2 halo rows per `seg` rows.
 // Halo rows above/below the band come from halo_top/halo_bot -- possibly another GPU's memory (NVLink) -- or are the
 // replicated edge row (gaussian_kernel.cl:57).
+//
+// The same kernel runs in FEED mode: instead of one (in, out, n_images) triple per launch, the groups are spread over
+// a ring of per-batch descriptors that the host appends to (b200blur_feed_*), every batch completes individually (a
+// flag in host-mapped memory) and the kernel stays resident until the feed is closed.  That is the reference's
+// `batch_size` loop (heterogeneous_blur.c:418-539: stage a batch, enqueue it, wait for it) without a kernel launch per
+// batch: at 35 images per batch a launch would carry ~2.4 us of HBM work, at 1 image 60 ns.
 struct StreamParams {
     BandParams b;
     int cpr;            // 16-byte chunks per row
     int cb;             // chunks per column block (<= blockDim.x)
     int ncb;            // column blocks per row
     int ipc;            // images side by side in one CTA step (ncb == 1 only)
-    int seg;            // output rows per item
-    int nseg;           // segments per band
-    int margin;         // 0 (full-width rows, contiguous copies) or 16 (column blocks, per-row copies)
-    int sstride;        // shared-memory row stride in bytes = cb*16 + 2*margin
+    int seg;            // output rows per group (coarse groups)
+    int nseg;           // coarse segments per band
+    int margin;         // 0 (whole rows, contiguous copies) or 16 (per-row copies: column blocks, heavily padded rows)
+    int sstride;        // shared-memory row stride in bytes = cb*16 + 2*margin, or the row pitch when margin == 0
     int slot_bytes;     // ipc * RB * sstride
     long long img_blocks;   // ceil(n_images / ipc)
-    long long n_groups;     // img_blocks * nseg * ncb
+    // Guided tail: image blocks [0, ib_coarse) are cut into `nseg` segments of `seg` rows, the remaining image blocks --
+    // the last work handed out -- into `nseg_fine` segments of `seg_fine` rows, so that the CTAs run dry within a
+    // fraction of a coarse group's time of each other instead of a whole one.
+    long long ib_coarse;
+    long long g_coarse;     // ib_coarse * nseg * ncb: first fine group
+    int seg_fine, nseg_fine;
+    long long n_groups;     // g_coarse + (img_blocks - ib_coarse) * nseg_fine * ncb
     unsigned long long *work;  // work[0] = next group to hand out, work[1] = CTAs finished (both 0 between launches)
     // Right edge of a row that does not end on a chunk boundary (row_bytes % 16 != 0, pitched rows).  The clamp
     // "pixel width := pixel width-1" means window bytes [row_bytes, row_bytes + C) := bytes [row_bytes - C, row_bytes).
@@ -242,7 +254,26 @@ struct StreamParams {
     int edge_prev;             // 1: the chunk before the last one needs its wr word patched too
     uint32_t sel_last[6];      // PRMT selectors for window words 0..5 of the last chunk (pairs: previous word, word)
     uint32_t sel_prev;         // PRMT selector for the wr word of the chunk before the last
+    // ---- FEED mode (template FEED = true); b.in / b.out / b.n_images are unused, every batch brings its own
+    const struct FeedBatch *batches;   // ring of `feed_cap` descriptors in device memory, written by the host's copies
+    unsigned long long *feed_ctl;      // [0] = batches published so far (tail), [1] = closed, [2] = watchdog tripped
+    unsigned int *feed_count;          // per ring slot: consumer-warp arrivals of the batch in it (0 between batches)
+    volatile unsigned int *feed_done;  // per ring slot, HOST-mapped: sequence number (low 32 bits, +1) of the batch completed
+    int feed_cap;                      // ring capacity (batches)
+    int feed_gpb;                      // group slots per batch = ceil(max_batch / ipc) * nseg * ncb (all coarse)
+    unsigned int feed_target;          // arrivals that complete a batch = feed_gpb * consumer warps
+    unsigned long long feed_timeout_ns;   // a CTA that waits this long for the host gives up (watchdog; 0 = never wait)
+    unsigned long long feed_base;      // sequence number of the batch in descriptor-ring position 0 of this launch
 };
+
+// One batch of a feed: `n_images` tight images starting at `in`, results to `out` (image stride = rows * pitch).
+struct FeedBatch {
+    const uint8_t *in;
+    uint8_t *out;
+    int n_images;
+    int pad_[3];
+};
+static_assert(sizeof(FeedBatch) == 32, "FeedBatch is copied as two 16-byte words");
 
 namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -272,6 +303,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)   // non-blocking
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 // 1-D bulk async copy global -> shared, completion (bytes) signalled on an mbarrier.  16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -291,41 +331,83 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+// Programmatic dependent launch: the next kernel in the stream may start its prologue while this one drains
+// (launch_dependents), and must not touch global memory before the previous kernel has completed and flushed (wait).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 }  // namespace ptx
 
-// Decodes group index -> geometry.  Groups are ordered image-block major, then segment, then column block, so CTAs
-// that run concurrently work on adjacent segments of the same images and the shared halo rows hit in L2.
+// What the producer knows about a group.  Groups are ordered image-block major, then segment, then column block, so
+// CTAs that run concurrently work on adjacent segments of the same images and the shared halo rows hit in L2.
 struct GroupGeom {
-    long long img0;   // first image of the group
-    int n_img;        // images in the group (<= ipc)
-    int r0;           // first output row
-    int nr;           // output rows
-    int x0;           // first byte column of the column block
-    int chunk0;       // index of its first chunk within the row
-    int cbe;          // chunks in this column block
+    const uint8_t *in;   // image lane 0 of the group: first row of the band
+    const uint8_t *top;  // image lane 0: halo row above the band, or nullptr (replicate)
+    const uint8_t *bot;
+    int n_img;           // images in the group (<= ipc)
+    int r0;              // first output row
+    int nr;              // output rows
+    int x0;              // first byte column of the column block
+    int cbe;             // chunks in this column block
     bool left_edge, right_edge;
 };
-__device__ __forceinline__ GroupGeom decode_group(const StreamParams &sp, long long g64)
+
+// What the consumers need to know about a group: written by the producer into shared memory next to the ring slot that
+// holds the group's first rows (the consumers never decode group indices themselves).
+struct __align__(16) GroupMeta {
+    uint8_t *out;        // image lane 0: output row r0, byte column x0
+    int n_img;           // < 0: no more work
+    int nr;
+    int cbe;
+    int flags;           // bit 0 left edge, bit 1 right edge, bit 2: chunk cbe-2 is the row's second-to-last chunk
+    int feed_slot;       // FEED: descriptor-ring slot of the batch this group belongs to
+    unsigned int feed_seq;   // FEED: value to publish in feed_done[feed_slot] when the batch completes
+};
+static_assert(sizeof(GroupMeta) == 32, "GroupMeta is read as two 16-byte words");
+
+// Segment/column decomposition of group `local` (an index within one image block's groups, or -- FEED -- one batch's).
+__device__ __forceinline__ void decode_rows_cols(const StreamParams &sp, unsigned sc, int seg, int rows, GroupGeom &q)
 {
-    GroupGeom q;
-    // n_groups < 2^31 (checked on the host: a group is at least a few KB), so 32-bit division -- inlined, no call
-    const unsigned g = (unsigned)g64;
-    const unsigned per_block = (unsigned)(sp.nseg * sp.ncb);
-    const unsigned ib = g / per_block;
-    const int sc = (int)(g - ib * per_block);
-    const int si = sc / sp.ncb;
-    const int ci = sc - si * sp.ncb;
-    q.img0 = (long long)ib * sp.ipc;
-    const long long left = sp.b.n_images - q.img0;
-    q.n_img = left < sp.ipc ? (int)left : sp.ipc;
-    q.r0 = si * sp.seg;
-    q.nr = min(sp.seg, sp.b.rows - q.r0);
+    const int si = (int)(sc / (unsigned)sp.ncb);
+    const int ci = (int)sc - si * sp.ncb;
+    q.r0 = si * seg;
+    q.nr = min(seg, rows - q.r0);
     q.x0 = ci * sp.cb * 16;
-    q.chunk0 = ci * sp.cb;
     q.cbe = min(sp.cb, sp.cpr - ci * sp.cb);
     q.left_edge = (ci == 0);
     q.right_edge = (ci == sp.ncb - 1);
-    return q;
+}
+
+__device__ __forceinline__ void decode_group(const StreamParams &sp, long long g64, GroupGeom &q, uint8_t *&out)
+{
+    // n_groups < 2^31 (checked on the host: a group is at least a few KB), so 32-bit division -- inlined, no call
+    unsigned ib, sc;
+    int seg;
+    if (g64 < sp.g_coarse) {
+        const unsigned g = (unsigned)g64, per_block = (unsigned)(sp.nseg * sp.ncb);
+        ib = g / per_block;
+        sc = g - ib * per_block;
+        seg = sp.seg;
+    } else {
+        const unsigned g = (unsigned)(g64 - sp.g_coarse), per_block = (unsigned)(sp.nseg_fine * sp.ncb);
+        ib = g / per_block;
+        sc = g - ib * per_block;
+        ib += (unsigned)sp.ib_coarse;
+        seg = sp.seg_fine;
+    }
+    decode_rows_cols(sp, sc, seg, sp.b.rows, q);
+    const long long img0 = (long long)ib * sp.ipc;
+    const long long left = sp.b.n_images - img0;
+    q.n_img = left < sp.ipc ? (int)left : sp.ipc;
+    q.in = sp.b.in + (size_t)img0 * sp.b.in_stride;
+    q.top = sp.b.halo_top ? sp.b.halo_top + (size_t)img0 * sp.b.top_stride : nullptr;
+    q.bot = sp.b.halo_bot ? sp.b.halo_bot + (size_t)img0 * sp.b.bot_stride : nullptr;
+    out = sp.b.out + (size_t)img0 * sp.b.out_stride + (size_t)q.r0 * sp.b.out_pitch + q.x0;
 }
 
 template <int RB>
@@ -342,8 +424,7 @@ __device__ __forceinline__ void stream_issue_slot(const StreamParams &sp, const 
     const uint32_t row_bytes = (uint32_t)(q.cbe * 16 + lm + rm);
     const uint32_t dst_col = (uint32_t)(sp.margin - lm);
     for (int il = 0; il < q.n_img; il++) {
-        const size_t img = (size_t)(q.img0 + il);
-        const uint8_t *src = b.in + img * b.in_stride;
+        const uint8_t *src = q.in + (size_t)il * b.in_stride;
         const uint32_t dst_img = slot_smem + (uint32_t)(il * RB * sp.sstride);
         int k = k0;
         while (k < k1) {
@@ -351,14 +432,14 @@ __device__ __forceinline__ void stream_issue_slot(const StreamParams &sp, const 
             const uint8_t *rp;
             int run = 1;
             if (j < 0) {
-                rp = b.halo_top ? b.halo_top + img * b.top_stride : src;
+                rp = q.top ? q.top + (size_t)il * b.top_stride : src;
             } else if (j >= b.rows) {
-                rp = b.halo_bot ? b.halo_bot + img * b.bot_stride : src + (size_t)(b.rows - 1) * b.pitch;
+                rp = q.bot ? q.bot + (size_t)il * b.bot_stride : src + (size_t)(b.rows - 1) * b.pitch;
             } else {
                 rp = src + (size_t)j * b.pitch;
                 if (sp.margin == 0) run = min(k1 - k, b.rows - j);  // contiguous rows: one copy
             }
-            // full-width: `run` whole rows as they lie in memory (padding included); a halo row brings only its live chunks
+            // whole rows: `run` rows as they lie in memory (padding included); a halo row brings only its live chunks
             const uint32_t bytes = (sp.margin != 0) ? row_bytes
                                    : (j < 0 || j >= b.rows) ? (uint32_t)sp.cpr * 16u : (uint32_t)run * (uint32_t)b.pitch;
             const uint32_t dst = dst_img + (uint32_t)((k - k0) * sp.sstride) + dst_col;
@@ -370,52 +451,203 @@ __device__ __forceinline__ void stream_issue_slot(const StreamParams &sp, const 
     ptx::mbar_arrive(bar);
 }
 
+// FEED: `n` consumer-warp arrivals for the batch in descriptor slot `slot`; the arrival that completes the batch
+// re-arms the slot's counter and publishes the batch's sequence number to the host.  The caller has fenced at GPU scope
+// after observing (through a CTA-scope mbarrier) that the consumer warps' stores of the group were issued -- the fence
+// is cumulative over them -- and the arrival that completes the batch fences at system scope before the host flag.
+__device__ __forceinline__ void feed_count_arrivals(const StreamParams &sp, int slot, unsigned int seq, unsigned int old,
+                                                    unsigned int n)
+{
+    if (old + n == sp.feed_target) {
+        sp.feed_count[slot] = 0;
+        __threadfence_system();
+        sp.feed_done[slot] = seq;
+    }
+}
+__device__ __forceinline__ void feed_arrive(const StreamParams &sp, int slot, unsigned int seq, unsigned int n)
+{
+    __threadfence();
+    feed_count_arrivals(sp, slot, seq, atomicAdd(sp.feed_count + slot, n), n);
+}
+
+constexpr int kFeedDepth = 8;   // group records in flight per CTA between producer, consumers and accountant (> NS)
+
 // Warp-specialised: warp 0 is the producer (one elected lane issues the bulk copies and never computes), warps 1..
 // are consumers.  full[NS] barriers carry the copies' byte counts; empty[NS] barriers collect one arrival per consumer
 // warp, so consumer warps never wait for each other -- only for data.
-// Work is handed out dynamically: the producer takes the next group from a global atomic counter and publishes its
-// index next to the slot (meta[]), so SMs that see more bandwidth simply take more groups.  (A static round-robin
-// persistent grid loses ~10 % of HBM bandwidth on B200 -- tools/membench.cu, profiles/membench_r01.txt.)
+// Work is handed out dynamically: the producer takes the next group from a global atomic counter and publishes what
+// the consumers need to know about it next to the slot (meta[]), so SMs that see more bandwidth simply take more
+// groups.  (A static round-robin persistent grid loses ~10 % of HBM bandwidth on B200 -- tools/membench.cu.)
 // EDGE = rows that do not end on a chunk boundary (pitched rows); compiled separately so the aligned case pays nothing.
-template <int C, int RB, int NS, bool EDGE = false>
-__global__ void __launch_bounds__(32 + 256)
+template <int C, int RB, int NS, bool EDGE = false, bool FEED = false>
+__global__ void __launch_bounds__((FEED ? 64 : 32) + 256)
 blur_stream_kernel(const StreamParams sp)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    // layout: [16 B pad][NS slots][16 B pad][NS full barriers][NS empty barriers][NS group indices]
+    // layout: [16 B pad][NS slots][16 B pad][NS full barriers][NS empty barriers][NS group records]
     const uint32_t ring = ptx::smem_u32(smem_raw) + 16;
     const uint32_t full = ring + (uint32_t)(NS * sp.slot_bytes) + 16;
     const uint32_t empty = full + 8 * NS;
-    volatile long long *meta = reinterpret_cast<volatile long long *>(smem_raw + 16 + (size_t)NS * sp.slot_bytes + 16 + 16 * NS);
+    GroupMeta *meta = reinterpret_cast<GroupMeta *>(smem_raw + 16 + (size_t)NS * sp.slot_bytes + 16 + 16 * NS);
+    // FEED: [kFeedDepth "group done" barriers][kFeedDepth "record free" barriers][kFeedDepth records {slot, seq}]
+    const uint32_t gdone = empty + 8 * NS + (uint32_t)sizeof(GroupMeta) * NS;
+    const uint32_t gfree = gdone + 8 * kFeedDepth;
+    int2 *grec = reinterpret_cast<int2 *>(reinterpret_cast<uint8_t *>(meta + NS) + 16 * kFeedDepth);
     const int t = threadIdx.x;
-    const int n_cwarps = (blockDim.x >> 5) - 1;
+    constexpr int LEAD = FEED ? 64 : 32;   // threads before the consumers: producer warp (+ accountant warp)
+    const int n_cwarps = ((int)blockDim.x - LEAD) >> 5;
     if (t == 0) {
         for (int i = 0; i < NS; i++) {
             ptx::mbar_init(full + 8 * i, 1);
             ptx::mbar_init(empty + 8 * i, n_cwarps);
         }
+        if (FEED)
+            for (int i = 0; i < kFeedDepth; i++) {
+                ptx::mbar_init(gdone + 8 * i, n_cwarps + 1);
+                ptx::mbar_init(gfree + 8 * i, 1);
+            }
         ptx::fence_barrier_init();
     }
     __syncthreads();
+    // Launched with programmatic stream serialisation: everything above overlapped the previous kernel's tail.
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
 
+    if (FEED && t >= 32 && t < 64) {
+        // ------------------------------------------------------------------ accountant warp (FEED only)
+        // Takes the completion of the groups off the consumers' path.  A GPU-scope fence waits for every store the SM
+        // has in flight -- microseconds while 12 consumer warps stream -- so a consumer warp that fenced once per group
+        // cost 30 % of the kernel's throughput, and one fence per group here would still be slower than the groups
+        // arrive.  The accountant therefore takes ALL groups whose consumer warps have arrived, fences once, and then
+        // adds each group's arrivals to its batch (the arrival that completes a batch raises the host flag).
+        if (t == 32) {
+            unsigned ga = 0;
+            for (bool stop = false; !stop;) {
+                int2 rec[kFeedDepth];
+                ptx::mbar_wait(gdone + 8 * (ga % kFeedDepth), (ga / kFeedDepth) & 1);
+                int n = 1;
+                while (n < kFeedDepth && ptx::mbar_test(gdone + 8 * ((ga + n) % kFeedDepth), ((ga + n) / kFeedDepth) & 1)) n++;
+#pragma unroll
+                for (int i = 0; i < kFeedDepth; i++)
+                    if (i < n) {
+                        rec[i] = grec[(ga + i) % kFeedDepth];
+                        ptx::mbar_arrive(gfree + 8 * ((ga + i) % kFeedDepth));
+                    }
+                ga += n;
+                __threadfence();
+                unsigned int old[kFeedDepth];
+#pragma unroll
+                for (int i = 0; i < kFeedDepth; i++)
+                    if (i < n && rec[i].x >= 0) old[i] = atomicAdd(sp.feed_count + rec[i].x, (unsigned)n_cwarps);
+#pragma unroll
+                for (int i = 0; i < kFeedDepth; i++)
+                    if (i < n) {
+                        if (rec[i].x < 0) stop = true;
+                        else feed_count_arrivals(sp, rec[i].x, (unsigned int)rec[i].y, old[i], (unsigned)n_cwarps);
+                    }
+            }
+        }
+        return;
+    }
     if (t < 32) {
         // ------------------------------------------------------------------ producer warp
         if (t == 0) {
             unsigned pcount = 0;
+            unsigned gp = 0;               // FEED: non-empty groups started by this CTA
+            unsigned long long tail = 0;   // FEED: batches known to be published
+            unsigned long long b_cur = 0, g_cur = 0;   // FEED: a batch this CTA has reached and its first group slot
             for (;;) {
                 const long long g = (long long)atomicAdd(sp.work, 1ull);
-                const bool done = g >= sp.n_groups;
+                bool done;
                 GroupGeom q;
+                GroupMeta m;
+                m.feed_slot = 0;
+                m.feed_seq = 0;
+                if (!FEED) {
+                    done = g >= sp.n_groups;
+                    if (!done) decode_group(sp, g, q, m.out);
+                } else {
+                    // group slot g belongs to batch g / feed_gpb of this launch; wait until the host has published it
+                    // (group slots only grow, so the batch index advances from the last one with a 32-bit division)
+                    const unsigned delta = (unsigned)((unsigned long long)g - g_cur);
+                    const unsigned db = delta / (unsigned)sp.feed_gpb;
+                    const unsigned local = delta - db * (unsigned)sp.feed_gpb;
+                    b_cur += db;
+                    g_cur += (unsigned long long)db * (unsigned)sp.feed_gpb;
+                    const unsigned long long b = b_cur;
+                    done = false;
+                    if (b >= tail) {
+                        const unsigned long long t0 = ptx::globaltimer_ns();
+                        for (;;) {
+                            tail = __ldcv(sp.feed_ctl);
+                            if (b < tail) break;
+                            if (__ldcv(sp.feed_ctl + 1)) {          // closed: the tail is final once `closed` is visible
+                                tail = __ldcv(sp.feed_ctl);
+                                done = b >= tail;
+                                break;
+                            }
+                            if (ptx::globaltimer_ns() - t0 > sp.feed_timeout_ns) {   // host gone: never hang the GPU
+                                atomicExch(sp.feed_ctl + 2, 1ull);
+                                sp.feed_done[sp.feed_cap] = 1u;
+                                __threadfence_system();
+                                done = true;
+                                break;
+                            }
+                            __nanosleep(256);
+                        }
+                        __threadfence();   // descriptors were written before the tail that covers them
+                    }
+                    if (!done) {
+                        const unsigned long long seq = sp.feed_base + b;
+                        const int slot = (int)(seq % (unsigned long long)sp.feed_cap);
+                        const uint4 *dp = reinterpret_cast<const uint4 *>(sp.batches + slot);
+                        const uint4 d0 = __ldcv(dp), d1 = __ldcv(dp + 1);
+                        const uint8_t *bin = reinterpret_cast<const uint8_t *>(((unsigned long long)d0.y << 32) | d0.x);
+                        uint8_t *bout = reinterpret_cast<uint8_t *>(((unsigned long long)d0.w << 32) | d0.z);
+                        const int n_images = (int)d1.x;
+                        const unsigned per_block = (unsigned)(sp.nseg * sp.ncb);
+                        const unsigned ib = local / per_block;
+                        const int img0 = (int)ib * sp.ipc;
+                        m.feed_slot = slot;
+                        m.feed_seq = (unsigned int)seq + 1u;
+                        if (img0 >= n_images) {               // a short batch: this group slot is empty
+                            feed_arrive(sp, slot, m.feed_seq, (unsigned)n_cwarps);
+                            continue;
+                        }
+                        decode_rows_cols(sp, local - ib * per_block, sp.seg, sp.b.rows, q);
+                        q.n_img = min(sp.ipc, n_images - img0);
+                        q.in = bin + (size_t)img0 * sp.b.in_stride;
+                        q.top = q.bot = nullptr;
+                        m.out = bout + (size_t)img0 * sp.b.out_stride + (size_t)q.r0 * sp.b.out_pitch + q.x0;
+                    }
+                }
+                if (FEED) {
+                    // hand the group's record to the accountant (or tell it to stop)
+                    const int i = gp % kFeedDepth;
+                    ptx::mbar_wait(gfree + 8 * i, ((gp / kFeedDepth) & 1) ^ 1);
+                    grec[i] = make_int2(done ? -1 : m.feed_slot, (int)m.feed_seq);
+                    for (int a = done ? n_cwarps + 1 : 1; a > 0; a--) ptx::mbar_arrive(gdone + 8 * i);
+                    gp++;
+                }
                 int nslots = 1;
                 if (!done) {
-                    q = decode_group(sp, g);
                     nslots = (q.nr + 2 + RB - 1) / RB;
+                    m.n_img = q.n_img;
+                    m.nr = q.nr;
+                    m.cbe = q.cbe;
+                    const int chunk0 = q.x0 >> 4;
+                    m.flags = (q.left_edge ? 1 : 0) | (q.right_edge ? 2 : 0) |
+                              ((EDGE && sp.edge_prev && chunk0 + q.cbe >= sp.cpr - 1) ? 4 : 0);
+                } else {
+                    m.out = nullptr;
+                    m.n_img = -1;
+                    m.nr = m.cbe = m.flags = 0;
                 }
                 for (int s = 0; s < nslots; s++, pcount++) {
                     const int buf = pcount % NS;
                     // wait until every consumer warp has released this buffer (passes at once on first use)
                     ptx::mbar_wait(empty + 8 * buf, ((pcount / NS) & 1) ^ 1);
-                    if (s == 0) meta[buf] = done ? -1 : g;
+                    if (s == 0) meta[buf] = m;
                     if (done) ptx::mbar_arrive(full + 8 * buf);   // sentinel slot: no data, tells the consumers to stop
                     else stream_issue_slot<RB>(sp, q, s, ring + (uint32_t)(buf * sp.slot_bytes), full + 8 * buf);
                 }
@@ -432,34 +664,33 @@ blur_stream_kernel(const StreamParams sp)
     }
 
     // ---------------------------------------------------------------------- consumer warps
-    const int ct = t - 32;
+    const int ct = t - LEAD;
     const int il = ct / sp.cb;           // image lane within the group
     const int c = ct - il * sp.cb;       // chunk within the column block
     const int lane = t & 31;
     unsigned ccount = 0;                 // slots consumed so far
+    unsigned gc = 0;                     // FEED: groups finished by this warp
     for (;;) {
-        // the first slot of an item carries the group index
+        // the first slot of an item carries the group record
         ptx::mbar_wait(full + 8 * (ccount % NS), (ccount / NS) & 1);
-        const long long g = meta[ccount % NS];
-        if (g < 0) break;
-        const GroupGeom q = decode_group(sp, g);
-        const bool active = (il < q.n_img) && (c < q.cbe);
-        const bool first = q.left_edge && (c == 0);
-        const bool last = q.right_edge && (c == q.cbe - 1);               // the chunk that holds the end of the row
-        const bool prev_last = EDGE && sp.edge_prev && (q.chunk0 + c == sp.cpr - 2);
-        const int nslots = (q.nr + 2 + RB - 1) / RB;
+        const GroupMeta m = meta[ccount % NS];
+        if (m.n_img < 0) break;
+        const bool active = (il < m.n_img) && (c < m.cbe);
+        const bool first = (m.flags & 1) && (c == 0);
+        const bool last = (m.flags & 2) && (c == m.cbe - 1);               // the chunk that holds the end of the row
+        const bool prev_last = EDGE && (m.flags & 4) && (c == m.cbe - 2);
+        const int nslots = (m.nr + 2 + RB - 1) / RB;
         const int il_c = active ? il : 0, c_c = active ? c : 0;
         const uint32_t lane_off = (uint32_t)(il_c * RB * sp.sstride + sp.margin + c_c * 16);
         // Output row k-2 is produced when input row k of the item arrives; the store pointer starts two rows early
         // and advances every row so the loop body has no branches (stores for k < 2 and k >= nr+2 are predicated off).
-        uint8_t *dst = sp.b.out + (size_t)(q.img0 + il_c) * sp.b.out_stride + (size_t)q.r0 * sp.b.out_pitch + q.x0 + c_c * 16 -
-                       2 * (ptrdiff_t)sp.b.out_pitch;
+        uint8_t *dst = m.out + (size_t)il_c * sp.b.out_stride + c_c * 16 - 2 * (ptrdiff_t)sp.b.out_pitch;
         // Rolling vertical state, pre-scaled by 16: before row k arrives
         //   accA = 16*(h[k-2] + 2*h[k-1])   accB = 16*h[k-1]        (<= 48960 per 16-bit lane)
         uint32_t accA[8], accB[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) accA[i] = accB[i] = 0;
-        const int k_end = q.nr + 2;
+        const int k_end = m.nr + 2;
         int k = 0;  // input-row index within the item
         for (int s = 0; s < nslots; s++, ccount++) {
             const int buf = ccount % NS;
@@ -503,6 +734,12 @@ blur_stream_kernel(const StreamParams sp)
             }
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(empty + 8 * buf);   // this warp is done reading the slot
+        }
+        if (FEED) {
+            // this warp's stores of the group are issued: arrive (release, CTA scope) for the accountant
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(gdone + 8 * (gc % kFeedDepth));
+            gc++;
         }
     }
 }

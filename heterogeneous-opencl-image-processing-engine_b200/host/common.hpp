@@ -115,7 +115,11 @@ struct ExtraOptions {
     bool checksum = false;    // --checksum                (FNV-1a of all outputs, end-to-end mode)
     int repeat = 1;           // --repeat R                (resident mode: passes over the stream)
     bool host_halo = false;   // --host-halo               (Approach 2: upload halo rows from the host like the reference)
-    int fill_threads = 4;     // --fill-threads T          (host threads per GPU that replicate the source image into staging)
+    int fill_threads = 0;     // --fill-threads T          (host threads per GPU that replicate the source image into staging; 0 = auto)
+    int ring = 4;             // --ring R                  (pinned + device slots per GPU in the end-to-end pipeline, >= 2)
+    bool oversubscribe = false;  // --oversubscribe        (allow --gpus G > visible devices: band/shard k runs on device k % visible;
+                                 //                          exercises the multi-GPU host logic on a single-GPU box)
+    bool static_split = false;   // --static-split         (Approach 1: fixed even partition per batch instead of work stealing)
 };
 
 inline int parse_extra(int argc, char **argv, int first, ExtraOptions &o)
@@ -138,9 +142,12 @@ inline int parse_extra(int argc, char **argv, int first, ExtraOptions &o)
         else if (a == "--repeat") o.repeat = atoi(val("--repeat"));
         else if (a == "--host-halo") o.host_halo = true;
         else if (a == "--fill-threads") o.fill_threads = atoi(val("--fill-threads"));
+        else if (a == "--ring") o.ring = atoi(val("--ring"));
+        else if (a == "--oversubscribe") o.oversubscribe = true;
+        else if (a == "--static-split") o.static_split = true;
         else { printf("Error: unknown option %s\n", a.c_str()); return -1; }
     }
-    if (o.width < 1 || o.height < 1 || o.num_images < 1 || o.repeat < 1) { printf("Error: bad size option\n"); return -1; }
+    if (o.width < 1 || o.height < 1 || o.num_images < 1 || o.repeat < 1 || o.ring < 2 || o.ring > 64) { printf("Error: bad size option\n"); return -1; }
     return 0;
 }
 
@@ -173,6 +180,15 @@ inline void replicate_rows(unsigned char *dst, const unsigned char *src, size_t 
     for (int t = 1; t < threads; t++) pool.emplace_back(work, count * t / threads, count * (t + 1) / threads);
     work(0, count / threads);
     for (auto &t : pool) t.join();
+}
+
+// Staging threads per GPU when --fill-threads is not given: the host cores shared out over the GPUs, 2..8 each
+// (one core copies ~14 GB/s with ordinary stores; a GPU's host link takes 45-55 GB/s).
+inline int auto_fill_threads(int gpus)
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    int t = (int)(hw ? hw : 8) / (gpus > 0 ? gpus : 1);
+    return t < 2 ? 2 : (t > 8 ? 8 : t);
 }
 
 struct DeviceTimes {

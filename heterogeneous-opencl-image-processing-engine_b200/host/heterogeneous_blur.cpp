@@ -120,7 +120,8 @@ int main(int argc, char **argv)
     }
     printf("Platform 0: NVIDIA CUDA (%s)\n", b200blur_version());
     int G = (mode == 0) ? n_dev : 1;  // cpu / gpu: one device; both: every visible GPU
-    if (opt.gpus > 0) G = std::min(opt.gpus, n_dev);
+    if (opt.gpus > 0) G = opt.oversubscribe ? opt.gpus : std::min(opt.gpus, n_dev);
+    if (opt.fill_threads <= 0) opt.fill_threads = auto_fill_threads(G);
     for (int k = 0; k < G; k++) {
         char dname[256];
         blur_check(b200blur_device_name(k, dname, sizeof dname), "Failed to get device name");

@@ -42,7 +42,6 @@ struct Worker {
     void *d_res_in = nullptr, *d_res_out = nullptr;
 };
 
-constexpr int kRing = 4;
 
 // Host-side rendezvous of the per-GPU threads.  With peer halos a band's kernel names its neighbours' upload events
 // and a band's next upload names its neighbours' kernel events; the two barriers per batch guarantee those event
@@ -79,6 +78,7 @@ int main(int argc, char **argv)
     int npos = 1;
     while (npos < argc && strncmp(argv[npos], "--", 2) != 0) npos++;
     if (parse_extra(argc, argv, npos, opt) != 0) return -1;
+    const int kRing = opt.ring;
     const int NUM_IMAGES = opt.num_images;
 
     if (npos > 1) {
@@ -127,8 +127,9 @@ int main(int argc, char **argv)
         return -1;
     }
     int G = n_dev;
-    if (opt.gpus > 0) G = std::min(opt.gpus, n_dev);
+    if (opt.gpus > 0) G = opt.oversubscribe ? opt.gpus : std::min(opt.gpus, n_dev);
     if (G > height) G = height;  // a band needs at least one row
+    if (opt.fill_threads <= 0) opt.fill_threads = auto_fill_threads(G);
 
     // ======================== CALCULATE SPLIT DIMENSIONS (split_image_blur.c:142-173) ========================
     if (height >= 2) {
@@ -159,9 +160,9 @@ int main(int argc, char **argv)
     printf("Platform 0: NVIDIA CUDA (%s)\n", b200blur_version());
     for (int k = 0; k < G; k++) {
         char dname[256];
-        blur_check(b200blur_device_name(k, dname, sizeof dname), "Failed to get device name");
+        blur_check(b200blur_device_name(k % n_dev, dname, sizeof dname), "Failed to get device name");
         printf("GPU device %d: %s\n", k, dname);
-        blur_check(b200blur_ctx_create(k, 3, &workers[k].ctx), "Failed to create context");
+        blur_check(b200blur_ctx_create(k % n_dev, 3, &workers[k].ctx), "Failed to create context");
     }
     if (!opt.host_halo)
         for (int k = 0; k + 1 < G; k++)

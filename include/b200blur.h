@@ -11,7 +11,11 @@
  * (A1 = heterogeneous_blur.c, A2 = split_image_blur.c, K = gaussian_kernel.cl).
  *
  * Threading: one host thread per GPU may call into distinct contexts concurrently (the reference is single
- * threaded with two asynchronous queues, A1:201-212).  A context must not be used by two threads at once.
+ * threaded with two asynchronous queues, A1:201-212).  A context must not be used by two threads at once, with ONE
+ * exception: b200blur_enqueue_wait_peer(ctx, queue, src, ev) may name an event of a context `src` that another
+ * thread is using at that moment.  That is safe because a context's event pool is fixed storage (slots are appended,
+ * never moved) and `ev` must be an event the owner has already enqueued and not yet released -- the caller orders
+ * that with its own host-side rendezvous (split_image_blur.cpp does, with two barriers per batch).
  * b200blur_last_error() is thread-local.
  */
 #ifndef B200BLUR_H
@@ -81,7 +85,8 @@ B200BLUR_API int b200blur_host_unregister(void *hptr);
 /* ------------------------------------------------------------------------------------------------- events
  * Every enqueue can return an event handle that records the command's start and end on the device, like the
  * cl_event of a PROFILING_ENABLE queue (A1:502-533).  event_ms = (END - START) in ms, the quantity summed at
- * A1:544-579.  Handles are small integers owned by the context; release returns them to its pool. */
+ * A1:544-579.  Handles are small integers owned by the context; release returns them to its pool (at most 32768
+ * live events per context, B200BLUR_ERR_NOMEM beyond; an enqueue that fails gives the event it took back). */
 typedef int32_t b200blur_event;
 #define B200BLUR_NO_EVENT ((b200blur_event *)0)
 B200BLUR_API int b200blur_event_ms(b200blur_ctx *ctx, b200blur_event ev, double *ms); /* clGetEventProfilingInfo */
@@ -93,7 +98,8 @@ B200BLUR_API int b200blur_events_elapsed_ms(b200blur_ctx *ctx, b200blur_event fr
 /* Make `queue` wait for the END of `ev` (cross-queue dependency; OpenCL's event wait list). */
 B200BLUR_API int b200blur_enqueue_wait(b200blur_ctx *ctx, int queue, b200blur_event ev);
 /* Same, for an event that belongs to ANOTHER context (another GPU): orders a band's kernel after its neighbours'
- * uploads when halo rows are read from peer memory.  The event must already have been enqueued by its owner. */
+ * uploads when halo rows are read from peer memory.  The event must already have been enqueued by its owner and must
+ * stay unreleased until this call returns; the owner may keep enqueueing other commands meanwhile (see Threading). */
 B200BLUR_API int b200blur_enqueue_wait_peer(b200blur_ctx *ctx, int queue, b200blur_ctx *src, b200blur_event ev);
 
 /* ----------------------------------------------------------------------------------------------- transfers
@@ -210,13 +216,16 @@ typedef struct b200blur_stats {
     int64_t d2h_bytes;
 } b200blur_stats;
 
-/* Device-resident: `d_in`/`d_out` hold n_images tight images in HBM.  Images are processed `batch_size` at a
- * time in stream order; when `coalesce` != 0 consecutive batches are fused into as few launches as possible
- * (they are independent), otherwise one launch per batch like the reference's per-batch sync (A1:538).  In the
- * per-batch form the launches are spread over ALL queues of the context (forked from and joined back into queue 0,
- * so the call still orders like one operation on queue 0) and a repeated identical request is replayed as a CUDA
- * graph.  stats == NULL makes the call asynchronous (no host synchronisation).  Widths with width*channels % 16 != 0
- * are re-pitched through a scratch pair owned by the context so that they still run on the vectorised kernel. */
+/* Device-resident: `d_in`/`d_out` hold n_images tight images in HBM.  Images are processed `batch_size` at a time:
+ *   coalesce == 1  consecutive batches are fused into as few launches as possible (they are independent);
+ *   coalesce == 0  one work descriptor per batch through the feed kernel (see b200blur_feed_*): one kernel launch per
+ *                  call, work units never span batches, every batch completes on its own like the reference's
+ *                  per-batch sync (A1:538); a repeated identical request re-uses the descriptor table on the device;
+ *   coalesce == 2  one kernel LAUNCH per batch, spread over all queues of the context (forked from and joined back
+ *                  into queue 0) and replayed as a CUDA graph when repeated -- the launch-bound form, kept to measure.
+ * The call orders like one operation on queue 0.  stats == NULL makes it asynchronous (no host synchronisation).
+ * Widths with width*channels % 16 != 0 are re-pitched through a scratch pair owned by the context so that they still
+ * run on the vectorised kernel. */
 B200BLUR_API int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int width, int height,
                                        int channels, int64_t n_images, int batch_size, int coalesce,
                                        b200blur_stats *stats);
@@ -227,6 +236,39 @@ B200BLUR_API int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void
  * reports the kernels actually launched.  Odd widths are re-pitched by the strided copies on the way in and out. */
 B200BLUR_API int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int width, int height,
                                    int channels, int64_t n_images, int batch_size, b200blur_stats *stats);
+
+/* ---------------------------------------------------------------------------------------------------- feed
+ * The batch loop of A1:418-600 as a RESIDENT kernel: instead of one kernel launch per batch (per image in the
+ * reference, A1:507), one persistent kernel per GPU pulls per-batch descriptors from a ring the host appends to and
+ * reports every batch's completion individually.  `batch_size` keeps the reference's meaning -- the unit the host
+ * stages, submits and waits for (A1:431-442, :482-539) -- without a launch per batch: at 35 images a launch carries
+ * ~2.4 us of HBM work, at 1 image 60 ns, far below launch latency.
+ *
+ *   create(ctx, W, H, C, max_batch, capacity)  geometry is fixed per feed; batches hold 1..max_batch tight images
+ *   start                                      launches the resident kernel on the feed's own stream
+ *   submit(d_in, d_out, n) -> ticket           stages one batch descriptor (device pointers, 16-byte aligned); blocks only
+ *                                              when `capacity` batches are in flight
+ *   flush                                      publishes everything staged so far to the kernel (two small async copies)
+ *   wait(ticket) / completed(ticket)           clFinish for ONE batch: its output is complete and visible to the host,
+ *                                              to copies and to kernels enqueued afterwards
+ *   stop                                       publishes, lets the kernel drain and exit; start may be called again
+ * Ordering with other work is by the host: submit a batch after its input is in place (e.g. after b200blur_event_ms /
+ * b200blur_finish on the upload), read its output after wait().  A kernel that sees no new batch for
+ * B200BLUR_FEED_TIMEOUT_MS (default 5000) stops by itself and the feed reports B200BLUR_ERR_CUDA -- a dead host never
+ * hangs the GPU.  While a feed runs its CTAs occupy the SMs: other kernels on the device wait for it to stop, and so do
+ * calls that wait for an idle device (dev_alloc / dev_free: allocate before start).  Copies on other queues proceed.
+ * Needs channels <= 4 and width*channels >= 256 and a multiple of 16 (else B200BLUR_ERR_INVALID: use enqueue_blur). */
+typedef struct b200blur_feed b200blur_feed;
+B200BLUR_API int b200blur_feed_create(b200blur_ctx *ctx, int width, int height, int channels, int max_batch_images,
+                                      int capacity, b200blur_feed **feed);
+B200BLUR_API int b200blur_feed_destroy(b200blur_feed *feed);
+B200BLUR_API int b200blur_feed_start(b200blur_feed *feed);
+B200BLUR_API int b200blur_feed_submit(b200blur_feed *feed, const void *d_in, void *d_out, int n_images, int64_t *ticket);
+B200BLUR_API int b200blur_feed_flush(b200blur_feed *feed);
+B200BLUR_API int b200blur_feed_wait(b200blur_feed *feed, int64_t ticket);
+B200BLUR_API int b200blur_feed_completed(b200blur_feed *feed, int64_t ticket, int *done);
+B200BLUR_API int b200blur_feed_stop(b200blur_feed *feed);
+B200BLUR_API int64_t b200blur_feed_submitted(const b200blur_feed *feed);
 
 /* -------------------------------------------------------------------------------- multi-GPU (Approach 2 bands)
  * No reference counterpart: the reference's devices only meet in host memory (A2:511-517). */

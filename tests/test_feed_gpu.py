@@ -1,0 +1,170 @@
+"""GPU tests of the feed (b200blur_feed_*): the reference's batch loop (heterogeneous_blur.c:418-539 -- stage a batch,
+enqueue it, wait for it) as ONE resident kernel that pulls per-batch descriptors from a ring the host appends to.
+Every result is compared bit-exactly with the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import b200blur
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def synth(seed, n, h, w, c=3):
+    return np.random.default_rng(seed).integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    oracle.build()
+    c = b200blur.Context(0, 4)
+    yield c
+    c.close()
+
+
+def _upload(ctx, x):
+    d_in, d_out = ctx.dev_alloc(x.nbytes), ctx.dev_alloc(x.nbytes)
+    ctx.enqueue_write(0, d_in, x, x.nbytes)
+    ctx.enqueue_write(0, d_out, np.zeros_like(x), x.nbytes)
+    ctx.finish(0)
+    return d_in, d_out
+
+
+def _download(ctx, d, like):
+    out = np.empty_like(like)
+    ctx.enqueue_read(0, out, d, like.nbytes)
+    ctx.finish(0)
+    return out
+
+
+@pytest.mark.parametrize("n,h,w,c,batch", [(70, 24, 320, 3, 35), (37, 40, 256, 3, 5), (9, 33, 128, 3, 1), (50, 16, 96, 3, 7),
+                                           (12, 64, 64, 4, 4), (11, 9, 512, 1, 3), (6, 12, 1408, 3, 2)])
+def test_feed_batches_match_oracle(ctx, n, h, w, c, batch):
+    """Batches of different sizes (the last one short), descriptors published in several flushes, tickets waited for
+    out of order; the output of a completed batch is read back while later batches are still running."""
+    x = synth(n * 3 + w, n, h, w, c)
+    want = oracle.c_blur_batch(x, integer=True)
+    d_in, d_out = _upload(ctx, x)
+    img = h * w * c
+    with ctx.feed(w, h, c, batch, capacity=4) as feed:       # small ring: submit must recycle descriptor slots
+        feed.start()
+        tickets = []
+        for i0 in range(0, n, batch):
+            m = min(batch, n - i0)
+            tickets.append((feed.submit(d_in + i0 * img, d_out + i0 * img, m), i0, m))
+            if len(tickets) % 3 == 0:
+                feed.flush()
+        assert [t for t, _, _ in tickets] == list(range(len(tickets)))
+        first = tickets[0]
+        feed.wait(first[0])                                    # flushes what is still staged
+        got0 = np.empty((first[2], h, w, c), np.uint8)
+        ctx.enqueue_read(1, got0, d_out + first[1] * img, got0.nbytes)
+        ctx.finish(1)
+        assert np.array_equal(got0, want[first[1]:first[1] + first[2]])
+        for t, _, _ in reversed(tickets):
+            feed.wait(t)
+            assert feed.completed(t)
+        feed.stop()
+    assert np.array_equal(_download(ctx, d_out, x), want)
+    ctx.dev_free(d_in)
+    ctx.dev_free(d_out)
+
+
+def test_feed_restart_and_distinct_buffers(ctx):
+    """Two runs of one feed (start/stop twice); every batch has its own device allocations, like the reference's
+    per-batch malloc (heterogeneous_blur.c:431-432) -- allocated BEFORE the feed starts (cudaMalloc/cudaFree wait for
+    the device to go idle, which a resident kernel never does); uploads and downloads run while the kernel is resident."""
+    h, w, c, batch = 30, 320, 3, 8
+    sizes = [batch if b % 3 else batch - 3 for b in range(10)]
+    bufs = [(ctx.dev_alloc(m * h * w * c), ctx.dev_alloc(m * h * w * c)) for m in sizes]
+    with ctx.feed(w, h, c, batch, capacity=16) as feed:
+        for run in range(2):
+            feed.start()
+            work = []
+            for b, m in enumerate(sizes):
+                x = synth(100 * run + b, m, h, w, c)
+                d_in, d_out = bufs[b]
+                ctx.enqueue_write(0, d_in, x, x.nbytes)
+                ctx.finish(0)                                   # the batch's input is in place before it is submitted
+                work.append((feed.submit(d_in, d_out, m), x, d_out))
+            feed.flush()
+            for t, x, d_out in work:
+                feed.wait(t)
+                assert np.array_equal(_download(ctx, d_out, x), oracle.c_blur_batch(x, integer=True))
+            feed.stop()
+        assert feed.submitted == 20
+    for d_in, d_out in bufs:
+        ctx.dev_free(d_in)
+        ctx.dev_free(d_out)
+
+
+def test_feed_rejects_what_it_cannot_run(ctx):
+    with pytest.raises(b200blur.BlurError):
+        ctx.feed(250, 37, 3, 8)            # rows of 750 bytes: not a multiple of 16
+    with pytest.raises(b200blur.BlurError):
+        ctx.feed(16, 16, 3, 8)             # rows shorter than 256 bytes
+    with ctx.feed(320, 8, 3, 4) as feed:
+        d = ctx.dev_alloc(4 * 8 * 320 * 3 * 2)
+        with pytest.raises(b200blur.BlurError):
+            feed.submit(d, d, 4)           # in place
+        with pytest.raises(b200blur.BlurError):
+            feed.submit(d, d + 4 * 8 * 960, 5)   # more images than max_batch
+        with pytest.raises(b200blur.BlurError):
+            feed.flush()                   # not running
+        t = feed.submit(d, d + 4 * 8 * 960, 4)
+        with pytest.raises(b200blur.BlurError):
+            feed.wait(t)                   # not running: cannot complete
+        feed.start()
+        feed.wait(t)
+        feed.stop()
+        ctx.dev_free(d)
+
+
+def test_feed_watchdog_stops_an_abandoned_kernel(ctx):
+    """A resident kernel whose host stops feeding it (and never stops it) gives up after the timeout instead of
+    occupying the GPU for ever; the feed then reports the failure."""
+    os.environ["B200BLUR_FEED_TIMEOUT_MS"] = "300"
+    try:
+        feed = ctx.feed(320, 8, 3, 4)
+    finally:
+        del os.environ["B200BLUR_FEED_TIMEOUT_MS"]
+    import time
+    feed.start()
+    time.sleep(1.0)
+    d = ctx.dev_alloc(2 * 4 * 8 * 960)
+    t = feed.submit(d, d + 4 * 8 * 960, 4)
+    with pytest.raises(b200blur.BlurError):
+        feed.wait(t)
+    with pytest.raises(b200blur.BlurError):
+        feed.submit(d, d + 4 * 8 * 960, 4)
+    feed.close()
+    ctx.dev_free(d)
+    # the context is still healthy
+    x = synth(1, 2, 8, 320, 3)
+    assert np.array_equal(ctx.blur_numpy(x), oracle.c_blur_batch(x))
+
+
+@pytest.mark.parametrize("n,batch", [(5000, 35), (300, 1), (1000, 500), (64, 64), (65, 64)])
+def test_run_resident_per_batch_descriptors(ctx, n, batch):
+    """b200blur_run_resident(coalesce=0): the batches go through the feed kernel as a descriptor table (one launch per
+    call), repeated calls re-use the table; == fused batches == one launch per batch (coalesce=2) == oracle sample."""
+    import torch
+    h, w, c = 240, 320, 3
+    g = torch.Generator(device="cuda").manual_seed(n + batch)
+    d_in = torch.randint(0, 256, (n, h, w, c), dtype=torch.uint8, device="cuda", generator=g)
+    fused, per_batch, per_launch = torch.zeros_like(d_in), torch.zeros_like(d_in), torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    ctx.run_resident(d_in, fused, w, h, c, n, batch, 1)
+    for _ in range(3):                                           # 2nd and 3rd call: table already on the device
+        per_batch.zero_()
+        torch.cuda.synchronize()
+        st = ctx.run_resident(d_in, per_batch, w, h, c, n, batch, 0)
+        assert st.launches == (1 if n > batch else st.launches)
+        assert torch.equal(per_batch, fused)
+    ctx.run_resident(d_in, per_launch, w, h, c, n, batch, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(per_launch, fused)
+    idx = sorted({0, n // 2, n - 1})
+    assert np.array_equal(fused[idx].cpu().numpy(), oracle.c_blur_batch(d_in[idx].cpu().numpy(), integer=True))

@@ -301,6 +301,33 @@ def test_pitched_rows_run_any_width_on_the_vectorised_path(ctx, shape):
     assert_same(_blur_pitched(ctx, x, extra_pitch=48), want)
 
 
+@pytest.mark.parametrize("shape,pitch", [((3, 21, 86, 3), 1024), ((2, 19, 256, 3), 4096), ((3, 9, 100, 3), 4096),
+                                         ((2, 40, 320, 3), 3840), ((2, 11, 128, 2), 1024), ((2, 6, 1400, 3), 16384)])
+def test_heavily_padded_rows(ctx, shape, pitch):
+    """ROI views / rows padded to several times width*channels (round-1 advisor finding: the streamed kernel sized its
+    shared-memory ring from the pitch and refused these).  Such rows bring only their live chunks, one copy per row."""
+    n, h, w, c = shape
+    assert pitch >= 3 * w * c or pitch >= 4096
+    x = synth(sum(shape) + pitch, n, h, w, c)
+    assert_same(_blur_pitched(ctx, x, extra_pitch=pitch - (w * c + 15) // 16 * 16), oracle.c_blur_batch(x))
+
+
+def test_failed_launch_releases_its_event(ctx):
+    """An enqueue that fails after taking a profiling event gives the slot back (no leak): many failures in a row must
+    not exhaust the pool, and the next good launch still gets an event."""
+    d = ctx.dev_alloc(4096)
+    for _ in range(40000):                                   # > the pool's capacity (32768)
+        with pytest.raises(b200blur.BlurError):
+            ctx.enqueue_blur(0, ctx.launch_rows(d, d, 16, 4, 3, 0, 4, 1), want_event=True)   # in place: rejected
+    bad = ctx.launch_rows(d, d + 2048, 16, 4, 3, 0, 4, 1)
+    bad.reserved = 1
+    with pytest.raises(b200blur.BlurError):
+        ctx.enqueue_blur(0, bad, want_event=True)
+    ev = ctx.enqueue_blur(0, ctx.launch_rows(d, d + 2048, 16, 4, 3, 0, 4, 1), want_event=True)
+    assert ctx.event_ms(ev) >= 0.0
+    ctx.dev_free(d)
+
+
 @pytest.mark.parametrize("n,h,w,c", [(300, 37, 250, 3), (40, 100, 341, 3), (3, 700, 1366, 3)])
 def test_run_resident_repitches_odd_widths(ctx, n, h, w, c):
     import torch
