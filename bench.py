@@ -550,7 +550,7 @@ def run_b200_arm(args) -> None:
     # ---- Approach 2 over NVLink (multi-GPU lines only): configs[2], then a sample of configs[4]
     a2_split = a2_large = None
     if world > 1 and not args.no_extras:
-        a2_split = run_a2(env, ctx, 5000, 256, 256, args.steps, args.warmup,
+        a2_split = run_a2(env, ctx, 5000, 256, 256, max(args.steps, 50), max(args.warmup, 5),   # (a step is only 40-160 us)
                           "A2 split-image: 5000x 256x256 RGB, row bands + 1-row halo over NVLink (BASELINE.json configs[2])")
         torch.cuda.empty_cache()
         a2_large = run_a2(env, ctx, 16, 8192, 8192, max(3, args.steps // 2), 2,

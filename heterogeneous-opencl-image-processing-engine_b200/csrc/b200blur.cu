@@ -418,8 +418,20 @@ int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, Str
         // slot makes small launches slower: 143 launches of 35 images take 0.85 ms with 6-row units, 0.44 ms with 24.)
         if (!feed)
             while (want > 6 && sp.img_blocks * sp.ncb * ((p.rows + want - 1) / want) < ctx->sm_count) want = (want + 1) / 2;
-        const long long nseg = (p.rows + want - 1) / want;
-        seg = (int)((p.rows + nseg - 1) / nseg);
+        // The consumers run whole ring slots (RB input rows) fully unrolled; a group of `seg` output rows reads seg + 2
+        // input rows, so seg + 2 = a multiple of RB keeps every slot of a full-height group whole.  Among the segment
+        // heights near `want`, take the one that processes the fewest input rows (2 halo rows per group) and leaves
+        // the fewest partly filled slots.
+        long long best = -1, best_cost = 0;
+        const long long lo = want * 3 / 4 > 6 ? want * 3 / 4 : 6, hi = want * 4 / 3 + 1;
+        for (long long sg = lo; sg <= hi && sg <= p.rows; sg++) {
+            const long long full_groups = p.rows / sg, rest = p.rows - full_groups * sg;
+            long long rows_in = full_groups * (sg + 2) + (rest ? rest + 2 : 0);
+            long long partial = full_groups * ((sg + 2) % cfg.rb ? 1 : 0) + (rest && (rest + 2) % cfg.rb ? 1 : 0);
+            const long long cost = rows_in * 16 + partial * 48 + (sg > want ? sg - want : want - sg);
+            if (best < 0 || cost < best_cost) { best = sg; best_cost = cost; }
+        }
+        seg = best > 0 ? (int)best : (int)(want < p.rows ? want : p.rows);
     }
     if (seg > p.rows) seg = p.rows;
     sp.seg = seg;

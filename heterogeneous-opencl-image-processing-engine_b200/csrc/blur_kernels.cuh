@@ -364,7 +364,7 @@ struct __align__(16) GroupMeta {
     int n_img;           // < 0: no more work
     int nr;
     int cbe;
-    int flags;           // bit 0 left edge, bit 1 right edge, bit 2: chunk cbe-2 is the row's second-to-last chunk
+    int flags;           // bit 0 left edge, bit 1 right edge, bits 8..: see the producer (second-to-last chunk of EDGE rows)
     int feed_slot;       // FEED: descriptor-ring slot of the batch this group belongs to
     unsigned int feed_seq;   // FEED: value to publish in feed_done[feed_slot] when the batch completes
 };
@@ -636,8 +636,11 @@ blur_stream_kernel(const StreamParams sp)
                     m.nr = q.nr;
                     m.cbe = q.cbe;
                     const int chunk0 = q.x0 >> 4;
+                    // bits 8..: 1 + the index within this column block of the row's second-to-last chunk, when that
+                    // chunk's right-neighbour word holds the end of the row (EDGE rows ending < 4 bytes into a chunk)
+                    const int pl = sp.cpr - 2 - chunk0;
                     m.flags = (q.left_edge ? 1 : 0) | (q.right_edge ? 2 : 0) |
-                              ((EDGE && sp.edge_prev && chunk0 + q.cbe >= sp.cpr - 1) ? 4 : 0);
+                              ((EDGE && sp.edge_prev && pl >= 0 && pl < q.cbe) ? (pl + 1) << 8 : 0);
                 } else {
                     m.out = nullptr;
                     m.n_img = -1;
@@ -678,60 +681,76 @@ blur_stream_kernel(const StreamParams sp)
         const bool active = (il < m.n_img) && (c < m.cbe);
         const bool first = (m.flags & 1) && (c == 0);
         const bool last = (m.flags & 2) && (c == m.cbe - 1);               // the chunk that holds the end of the row
-        const bool prev_last = EDGE && (m.flags & 4) && (c == m.cbe - 2);
+        const bool prev_last = EDGE && ((m.flags >> 8) == c + 1);
         const int nslots = (m.nr + 2 + RB - 1) / RB;
         const int il_c = active ? il : 0, c_c = active ? c : 0;
         const uint32_t lane_off = (uint32_t)(il_c * RB * sp.sstride + sp.margin + c_c * 16);
-        // Output row k-2 is produced when input row k of the item arrives; the store pointer starts two rows early
-        // and advances every row so the loop body has no branches (stores for k < 2 and k >= nr+2 are predicated off).
+        // Output row k-2 is produced when input row k of the item arrives: `dst` points two rows early.
         uint8_t *dst = m.out + (size_t)il_c * sp.b.out_stride + c_c * 16 - 2 * (ptrdiff_t)sp.b.out_pitch;
         // Rolling vertical state, pre-scaled by 16: before row k arrives
         //   accA = 16*(h[k-2] + 2*h[k-1])   accB = 16*h[k-1]        (<= 48960 per 16-bit lane)
         uint32_t accA[8], accB[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) accA[i] = accB[i] = 0;
+        // one input row: horizontal sums, vertical roll, one 16-byte store (if `store`)
+        auto row = [&](uint32_t a, uint8_t *out_row, bool store) {
+            uint4 w = ptx::lds128(a);
+            uint32_t wl = ptx::lds32(a - 4);
+            uint32_t wr = ptx::lds32(a + 16);
+            if (first) wl = w.x << (8 * (4 - C));   // clamp: pixel -1 := pixel 0        (gaussian_kernel.cl:56)
+            if (!EDGE) {
+                if (last) wr = w.w >> (8 * (4 - C));    // clamp: pixel width := pixel width-1
+            } else if (last) {                          // row ends inside this chunk: rewrite the window
+                const uint32_t n0 = __byte_perm(wl, w.x, sp.sel_last[1]), n1 = __byte_perm(w.x, w.y, sp.sel_last[2]);
+                const uint32_t n2 = __byte_perm(w.y, w.z, sp.sel_last[3]), n3 = __byte_perm(w.z, w.w, sp.sel_last[4]);
+                wr = __byte_perm(w.w, wr, sp.sel_last[5]);
+                w.x = n0; w.y = n1; w.z = n2; w.w = n3;
+            } else if (prev_last) {
+                wr = __byte_perm(w.w, wr, sp.sel_prev);
+            }
+            uint32_t h[8];
+            hpass8<C>(w, wl, wr, h);
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                v[i] = h[i] * 16u + accA[i];       // 16*(h[k-2] + 2*h[k-1] + h[k])  <= 65280 per lane
+                accA[i] = h[i] * 32u + accB[i];
+                accB[i] = h[i] << 4;
+            }
+            uint4 o;
+            o.x = __byte_perm(v[0], v[1], 0x7351);
+            o.y = __byte_perm(v[2], v[3], 0x7351);
+            o.z = __byte_perm(v[4], v[5], 0x7351);
+            o.w = __byte_perm(v[6], v[7], 0x7351);
+            if (store) stg128_stream(out_row, o);
+        };
         const int k_end = m.nr + 2;
         int k = 0;  // input-row index within the item
         for (int s = 0; s < nslots; s++, ccount++) {
             const int buf = ccount % NS;
             if (s > 0) ptx::mbar_wait(full + 8 * buf, (ccount / NS) & 1);
-            uint32_t a = ring + (uint32_t)(buf * sp.slot_bytes) + lane_off;
+            const uint32_t a = ring + (uint32_t)(buf * sp.slot_bytes) + lane_off;
+            // Whole slots (the planner sizes groups so that nearly all are) run fully unrolled with compile-time row
+            // offsets and no per-row trip test; the first slot of a group only differs in not storing rows 0 and 1.
+            if (k_end - k >= RB) {
+                if (s == 0) {
 #pragma unroll
-            for (int r = 0; r < RB; r++) {
-                if (k >= k_end) break;                  // short last slot of an item (uniform across the CTA)
-                uint4 w = ptx::lds128(a);
-                uint32_t wl = ptx::lds32(a - 4);
-                uint32_t wr = ptx::lds32(a + 16);
-                a += sp.sstride;
-                if (first) wl = w.x << (8 * (4 - C));   // clamp: pixel -1 := pixel 0        (gaussian_kernel.cl:56)
-                if (!EDGE) {
-                    if (last) wr = w.w >> (8 * (4 - C));    // clamp: pixel width := pixel width-1
-                } else if (last) {                          // row ends inside this chunk: rewrite the window
-                    const uint32_t n0 = __byte_perm(wl, w.x, sp.sel_last[1]), n1 = __byte_perm(w.x, w.y, sp.sel_last[2]);
-                    const uint32_t n2 = __byte_perm(w.y, w.z, sp.sel_last[3]), n3 = __byte_perm(w.z, w.w, sp.sel_last[4]);
-                    wr = __byte_perm(w.w, wr, sp.sel_last[5]);
-                    w.x = n0; w.y = n1; w.z = n2; w.w = n3;
-                } else if (prev_last) {
-                    wr = __byte_perm(w.w, wr, sp.sel_prev);
-                }
-                uint32_t h[8];
-                hpass8<C>(w, wl, wr, h);
-                uint32_t v[8];
+                    for (int r = 0; r < RB; r++)
+                        row(a + (uint32_t)r * (uint32_t)sp.sstride, dst + (size_t)r * (size_t)sp.b.out_pitch, active && r >= 2);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    v[i] = h[i] * 16u + accA[i];       // 16*(h[k-2] + 2*h[k-1] + h[k])  <= 65280 per lane
-                    accA[i] = h[i] * 32u + accB[i];
-                    accB[i] = h[i] << 4;
+                    for (int r = 0; r < RB; r++)
+                        row(a + (uint32_t)r * (uint32_t)sp.sstride, dst + (size_t)r * (size_t)sp.b.out_pitch, active);
                 }
-                uint4 o;
-                o.x = __byte_perm(v[0], v[1], 0x7351);
-                o.y = __byte_perm(v[2], v[3], 0x7351);
-                o.z = __byte_perm(v[4], v[5], 0x7351);
-                o.w = __byte_perm(v[6], v[7], 0x7351);
-                if (active && k >= 2) stg128_stream(dst, o);
-                dst += sp.b.out_pitch;
-                k++;
+                k += RB;
+            } else {
+                const int n = k_end - k;                // short last slot of a group (uniform across the CTA)
+#pragma unroll 1
+                for (int r = 0; r < n; r++)
+                    row(a + (uint32_t)r * (uint32_t)sp.sstride, dst + (size_t)r * (size_t)sp.b.out_pitch, active && k + r >= 2);
+                k += n;
             }
+            dst += (size_t)RB * (size_t)sp.b.out_pitch;
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(empty + 8 * buf);   // this warp is done reading the slot
         }

@@ -119,6 +119,7 @@ struct ExtraOptions {
     int ring = 4;             // --ring R                  (pinned + device slots per GPU in the end-to-end pipeline, >= 2)
     bool oversubscribe = false;  // --oversubscribe        (allow --gpus G > visible devices: band/shard k runs on device k % visible;
                                  //                          exercises the multi-GPU host logic on a single-GPU box)
+    int fuse = 0;                // --fuse N               (batches per transfer/launch; 0 = automatic ~64 MB, 1 = the reference's granularity)
     bool static_split = false;   // --static-split         (Approach 1: fixed even partition per batch instead of work stealing)
 };
 
@@ -145,6 +146,7 @@ inline int parse_extra(int argc, char **argv, int first, ExtraOptions &o)
         else if (a == "--ring") o.ring = atoi(val("--ring"));
         else if (a == "--oversubscribe") o.oversubscribe = true;
         else if (a == "--static-split") o.static_split = true;
+        else if (a == "--fuse") o.fuse = atoi(val("--fuse"));
         else { printf("Error: unknown option %s\n", a.c_str()); return -1; }
     }
     if (o.width < 1 || o.height < 1 || o.num_images < 1 || o.repeat < 1 || o.ring < 2 || o.ring > 64) { printf("Error: bad size option\n"); return -1; }
@@ -165,35 +167,129 @@ inline void load_source_image(const ExtraOptions &o, Image &img, std::string &na
     }
 }
 
-// The reference's "copy original image to each slot" loop (heterogeneous_blur.c:440-442), spread over a few host
-// threads: one core replicates at ~20 GB/s, the host link moves ~45-55 GB/s, so a single thread would be the bottleneck.
+// The reference's "copy original image to each slot" loop (heterogeneous_blur.c:440-442).  The source image stays in the
+// core's cache; the destination is pinned staging memory that the GPU's copy engine reads next and the CPU never reads
+// back, so the copy uses non-temporal stores: no read-for-ownership of the destination lines (a third less DRAM traffic
+// than memcpy) and no cache pollution.  Spread over a few host threads: one core streams ~10-14 GB/s, a GPU's host link
+// takes 45-55 GB/s.
 #include <thread>
-inline void replicate_rows(unsigned char *dst, const unsigned char *src, size_t bytes_each, long long count, int threads)
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+inline void copy_streaming(unsigned char *dst, const unsigned char *src, size_t n)
 {
-    if (threads < 1) threads = 1;
-    if (count < 2 * threads || (double)count * bytes_each < 8e6) threads = 1;
-    auto work = [&](long long a, long long b) {
-        for (long long i = a; i < b; i++) memcpy(dst + (size_t)i * bytes_each, src, bytes_each);
-    };
-    if (threads == 1) { work(0, count); return; }
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; t++) pool.emplace_back(work, count * t / threads, count * (t + 1) / threads);
-    work(0, count / threads);
-    for (auto &t : pool) t.join();
+    // head: up to the first 16-byte boundary of dst
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (head > n) head = n;
+    memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; i++) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst), a);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + 48), d);
+        src += 64; dst += 64;
+    }
+    memcpy(dst, src, n - blocks * 64);
 }
+inline void copy_streaming_done() { _mm_sfence(); }
+#else
+inline void copy_streaming(unsigned char *dst, const unsigned char *src, size_t n) { memcpy(dst, src, n); }
+inline void copy_streaming_done() {}
+#endif
 
-// Staging threads per GPU when --fill-threads is not given: the host cores shared out over the GPUs, 2..8 each
-// (one core copies ~14 GB/s with ordinary stores; a GPU's host link takes 45-55 GB/s).
+// A few persistent host threads per GPU worker that replicate the source image into a staging slot (a thread per
+// call would cost ~50 us each to create, 8 of them per 1 ms of copying).
+#include <condition_variable>
+#include <mutex>
+class StagingPool {
+public:
+    explicit StagingPool(int threads) : n_(threads < 1 ? 1 : threads)
+    {
+        for (int t = 1; t < n_; t++) pool_.emplace_back([this, t] { loop(t); });
+    }
+    ~StagingPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            quit_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto &t : pool_) t.join();
+    }
+    int threads() const { return n_; }
+    // dst[i] = src for i in [0, count): `count` copies of `bytes_each` bytes
+    void replicate(unsigned char *dst, const unsigned char *src, size_t bytes_each, long long count)
+    {
+        int use = n_;
+        if (count < 2 * use || (double)count * bytes_each < 4e6) use = 1;
+        if (use == 1) { work(dst, src, bytes_each, 0, count); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            dst_ = dst; src_ = src; each_ = bytes_each; count_ = count; use_ = use;
+            pending_ = use - 1;
+            gen_++;
+        }
+        cv_.notify_all();
+        work(dst, src, bytes_each, 0, count / use);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    static void work(unsigned char *dst, const unsigned char *src, size_t each, long long a, long long b)
+    {
+        for (long long i = a; i < b; i++) copy_streaming(dst + (size_t)i * each, src, each);
+        copy_streaming_done();
+    }
+    void loop(int t)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            unsigned char *dst; const unsigned char *src; size_t each; long long count; int use;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (quit_) return;
+                dst = dst_; src = src_; each = each_; count = count_; use = use_;
+            }
+            if (t < use) {
+                work(dst, src, each, count * t / use, count * (t + 1) / use);
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> pool_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    unsigned long long gen_ = 0;
+    bool quit_ = false;
+    unsigned char *dst_ = nullptr; const unsigned char *src_ = nullptr; size_t each_ = 0; long long count_ = 0;
+    int use_ = 1, pending_ = 0;
+};
+
+// Staging threads per GPU when --fill-threads is not given: a quarter of the host cores shared out over the GPUs,
+// 2..4 each.  More is slower: the staging stores compete with the copy engines for the same host memory (measured on a
+// 16-core box, one GPU, 5000 x 320x240: 4 threads 180 k images/s, 8 threads 171 k, 12 threads 170 k).
 inline int auto_fill_threads(int gpus)
 {
     const unsigned hw = std::thread::hardware_concurrency();
-    int t = (int)(hw ? hw : 8) / (gpus > 0 ? gpus : 1);
-    return t < 2 ? 2 : (t > 8 ? 8 : t);
+    int t = (int)(hw ? hw : 8) / (4 * (gpus > 0 ? gpus : 1));
+    return t < 2 ? 2 : (t > 4 ? 4 : t);
 }
 
 struct DeviceTimes {
     double in_ms = 0, kernel_ms = 0, out_ms = 0;
     double fill_ms = 0;  // host time spent replicating the source image into staging (inside the wall-clock window)
+    double busy_until_ms = 0;  // wall-clock time at which this GPU's last result was back on the host
     long long images = 0;
     double total() const { return in_ms + kernel_ms + out_ms; }
 };

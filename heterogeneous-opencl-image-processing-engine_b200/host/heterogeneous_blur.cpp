@@ -7,7 +7,11 @@
 // What changed underneath (BASELINE.json north_star):
 //   * devices   -- the CPU+iGPU pair becomes G B200s: `cpu` and `gpu` run on ONE GPU, `both` on all visible GPUs.
 //                  There is no CPU device any more, so `gpu_ratio` is accepted and echoed but the per-batch split
-//                  (int)(batch_count*gpu_ratio) of :449-451 is replaced by an even partition over the GPUs.
+//                  (int)(batch_count*gpu_ratio) of :449-451 is replaced: by default the GPUs TAKE work from a shared
+//                  counter (groups of whole batches, ~64 MB each), so a GPU that gets less of the box's shared host
+//                  link simply takes fewer -- the measured shares are what the reference's ratio recommendation
+//                  (:713-722) would have had to be tuned to by hand; --static-split keeps a fixed even partition of
+//                  every batch instead.
 //   * plumbing  -- every cl* call is the matching b200blur_* call (include/b200blur.h); the kernel is precompiled.
 //   * pipeline  -- per GPU one host thread, three queues (H2D / blur / D2H) and a ring of pinned + device slots, so
 //                  the write / kernel / read of different batches overlap instead of running back to back per image
@@ -15,6 +19,7 @@
 //   * kernel    -- one launch blurs a whole share of a batch (the reference launches once per image, :507).
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <thread>
 
 #include "common.hpp"
@@ -34,12 +39,11 @@ struct Worker {
     b200blur_ctx *ctx = nullptr;
     std::vector<Slot> ring;
     DeviceTimes t;
+    std::unique_ptr<StagingPool> staging;
     uint64_t checksum = 1469598103934665603ull;
     double resident_ms = 0;
     long long resident_launches = 0;
 };
-
-constexpr int kRing = 4;
 
 }  // namespace
 
@@ -55,6 +59,7 @@ int main(int argc, char **argv)
     int npos = 1;
     while (npos < argc && strncmp(argv[npos], "--", 2) != 0) npos++;  // positional arguments end at the first --flag
     if (parse_extra(argc, argv, npos, opt) != 0) return -1;
+    const int kRing = opt.ring;
     const int NUM_IMAGES = opt.num_images;
 
     if (npos > 1) {
@@ -124,32 +129,38 @@ int main(int argc, char **argv)
     if (opt.fill_threads <= 0) opt.fill_threads = auto_fill_threads(G);
     for (int k = 0; k < G; k++) {
         char dname[256];
-        blur_check(b200blur_device_name(k, dname, sizeof dname), "Failed to get device name");
+        blur_check(b200blur_device_name(k % n_dev, dname, sizeof dname), "Failed to get device name");
         printf("GPU device %d: %s\n", k, dname);
     }
     if (mode == 0 && npos > 2)
-        printf("Note: gpu_ratio %.3f is kept for CLI compatibility; images are partitioned evenly over %d GPU(s)\n", gpu_ratio, G);
+        printf("Note: gpu_ratio %.3f is kept for CLI compatibility; %s\n", gpu_ratio,
+               G > 1 && !opt.static_split && !opt.resident ? "the GPUs take groups of batches from a shared counter (work stealing)"
+                                                            : "images are partitioned evenly over the GPU(s)");
     printf("\n");
 
     // ======================== CONTEXTS / QUEUES / BUFFERS (:194-355) ========================
     printf("Kernel objects created (precompiled sm_100a, no gaussian_kernel.cl needed at run time)\n\n");
     printf("Allocating device buffers...\n");
     std::vector<Worker> workers(G);
+    const bool stealing = G > 1 && !opt.static_split && !opt.resident;
     long long max_share = 0;
     for (int k = 0; k < G; k++) {
         int64_t b, c;
         b200blur_partition(BATCH_SIZE, G, k, &b, &c);
         max_share = std::max<long long>(max_share, c);
     }
-    // Batches are independent, so a GPU's shares of `fuse` consecutive batches travel and launch together: ~64 MB per
-    // transfer keeps the host link at its ceiling (8 MB transfers reach only ~33 of 45 GB/s, tools/e2e.py).
+    if (stealing) max_share = BATCH_SIZE;   // a GPU takes whole batches
+    // Batches are independent, so `fuse` consecutive batches (a GPU's shares of them) travel and launch together: ~64 MB
+    // per transfer keeps the host link at its ceiling (8 MB transfers reach only ~33 of 45 GB/s, tools/e2e.py).
     long long fuse = (long long)((64.0 * 1024 * 1024) / ((double)max_share * image_size) + 0.5);
-    fuse = std::max(1LL, std::min<long long>(fuse, std::max(1, NUM_BATCHES / 16)));  // keep >= 16 pipeline steps per GPU
+    // keep >= 16 pipeline steps per GPU (and, when the GPUs take work dynamically, enough steps to balance them)
+    fuse = std::max(1LL, std::min<long long>(fuse, std::max(1, NUM_BATCHES / (stealing ? 16 * G : 16))));
+    if (opt.fuse > 0) fuse = opt.fuse;
     const long long slot_images = max_share * fuse;
     for (int k = 0; k < G; k++) {
         Worker &w = workers[k];
         w.gpu = k;
-        blur_check(b200blur_ctx_create(k, 3, &w.ctx), "Failed to create context");
+        blur_check(b200blur_ctx_create(k % n_dev, 3, &w.ctx), "Failed to create context");
         if (!opt.resident) {
             w.ring.resize(kRing);
             for (auto &s : w.ring) {
@@ -160,6 +171,21 @@ int main(int argc, char **argv)
             }
         }
     }
+    // Like the reference, whose program build (clBuildProgram, :257-322) happens before its timer starts: load the
+    // kernel image and wake the copy paths with one tiny write -> blur -> read per GPU, and start the staging threads.
+    if (!opt.resident)
+        for (auto &w : workers) {
+            w.staging.reset(new StagingPool(opt.fill_threads));
+            Slot &s = w.ring[0];
+            memcpy(s.h_in, original_image, image_size);
+            b200blur_launch l;
+            blur_check(b200blur_enqueue_write(w.ctx, 0, s.d_in, s.h_in, image_size, NULL), "GPU write failed");
+            blur_check(b200blur_launch_rows(&l, s.d_in, s.d_out, width, height, channels, 0, height, 1, image_size, image_size),
+                       "Failed to set kernel args");
+            blur_check(b200blur_enqueue_blur(w.ctx, 0, &l, NULL), "GPU kernel launch failed");
+            blur_check(b200blur_enqueue_read(w.ctx, 0, s.h_out, s.d_out, image_size, NULL), "GPU read failed");
+            blur_check(b200blur_finish_all(w.ctx), "finish failed");
+        }
     printf("Device buffers allocated\n\n");
     printf("Global work size: %d x %d per image, up to %lld image(s) per launch (%lld batch share(s) fused)\n",
            (width + 15) / 16 * 16, (height + 15) / 16 * 16, slot_images, fuse);
@@ -186,6 +212,8 @@ int main(int argc, char **argv)
         s.busy = false;
     };
 
+    std::atomic<long long> next_group{0};
+    std::vector<long long> issued_groups(G, 0);
     auto run_worker = [&](Worker &w) {
         const int k = w.gpu;
         if (opt.resident) {
@@ -226,25 +254,38 @@ int main(int argc, char **argv)
             return;
         }
         long long issued = 0;
-        for (int batch0 = 0; batch0 < NUM_BATCHES; batch0 += (int)fuse) {
-            // this GPU's shares of batches [batch0, batch0 + fuse)
+        for (;;) {
+            // next group of `fuse` batches: taken from the shared counter (work stealing), or every group in turn
+            // with this GPU's even share of each batch (--static-split)
+            long long batch0;
+            if (stealing) {
+                batch0 = next_group.fetch_add(1, std::memory_order_relaxed) * fuse;
+            } else {
+                batch0 = issued_groups[k] * fuse;
+                issued_groups[k]++;
+            }
+            if (batch0 >= NUM_BATCHES) break;
             long long count = 0, first_image = -1;
-            for (int batch = batch0; batch < std::min<long long>(NUM_BATCHES, batch0 + fuse); batch++) {
-                const int batch_start = batch * BATCH_SIZE;
-                int batch_count = BATCH_SIZE;
+            for (long long batch = batch0; batch < std::min<long long>(NUM_BATCHES, batch0 + fuse); batch++) {
+                const long long batch_start = batch * BATCH_SIZE;
+                long long batch_count = BATCH_SIZE;
                 if (batch_start + batch_count > NUM_IMAGES) batch_count = NUM_IMAGES - batch_start;  // :423-427
-                if (k == 0 && !opt.quiet) {
-                    printf("=== Processing Batch %d/%d ===\n", batch + 1, NUM_BATCHES);
-                    printf("  Batch work distribution:");
-                    for (int j = 0; j < G; j++) {
-                        int64_t b, c;
-                        b200blur_partition(batch_count, G, j, &b, &c);
-                        printf(" GPU%d=%lld", j, (long long)c);
+                if ((stealing || k == 0) && !opt.quiet) {
+                    if (stealing) {
+                        printf("=== Processing Batch %lld/%d === taken by GPU %d (%lld images)\n", batch + 1, NUM_BATCHES, k, batch_count);
+                    } else {
+                        printf("=== Processing Batch %lld/%d ===\n", batch + 1, NUM_BATCHES);
+                        printf("  Batch work distribution:");
+                        for (int j = 0; j < G; j++) {
+                            int64_t b, c;
+                            b200blur_partition(batch_count, G, j, &b, &c);
+                            printf(" GPU%d=%lld", j, (long long)c);
+                        }
+                        printf("\n");
                     }
-                    printf("\n");
                 }
-                int64_t begin, c;
-                b200blur_partition(batch_count, G, k, &begin, &c);  // replaces (int)(batch_count * gpu_ratio), :449-451
+                int64_t begin = 0, c = batch_count;
+                if (!stealing) b200blur_partition(batch_count, G, k, &begin, &c);  // replaces (int)(batch_count * gpu_ratio), :449-451
                 if (c > 0 && first_image < 0) first_image = batch_start + begin;
                 count += c;
             }
@@ -255,7 +296,7 @@ int main(int argc, char **argv)
             s.first_image = first_image;
             // CREATE BATCH IMAGE STREAM (:431-442): replicate the source image into this share's staging slots
             const double tf = get_time_ms();
-            replicate_rows(s.h_in, original_image, image_size, count, opt.fill_threads);
+            w.staging->replicate(s.h_in, original_image, image_size, count);
             w.t.fill_ms += get_time_ms() - tf;
             const size_t bytes = (size_t)count * image_size;
             blur_check(b200blur_enqueue_write(w.ctx, 0, s.d_in, s.h_in, bytes, &s.ev_in), "GPU write failed");
@@ -273,6 +314,7 @@ int main(int argc, char **argv)
         for (auto &s : w.ring)
             if (s.busy) harvest(w, s);
         blur_check(b200blur_finish_all(w.ctx), "finish failed");  // clFinish (:538-539)
+        w.t.busy_until_ms = get_time_ms();
     };
 
     const double time_start_total = get_time_ms();
@@ -299,11 +341,16 @@ int main(int argc, char **argv)
         printf("   Total wall-clock time: %.2f ms (%.2f seconds)\n", time_total_processing, time_total_processing / 1000.0);
     printf("   Total images processed: %lld\n\n", images_done);
 
+    // Section numbers: the reference prints 2 = CPU, 3 = GPU, 4..8 = comparison .. recommendation (:621-722).  With G
+    // GPUs the device sections are 2 .. G+1 and the rest follow; G = 2 gives the reference's numbers, a single GPU keeps
+    // the reference's "2" (cpu) / "3" (gpu) and its fixed "7. THROUGHPUT".
+    const int sec_base = G >= 2 ? G + 2 : 4;   // number of the DEVICE COMPARISON section
     for (int k = 0; k < G; k++) {
         const DeviceTimes &t = workers[k].t;
         if (t.images == 0) continue;
         const double tot = t.total();
-        printf("%d. GPU %d DEVICE (processed %lld images)\n", 2 + k, k, t.images);
+        printf("%d. GPU %d DEVICE (processed %lld images, %.1f%% of the stream)\n", G == 1 && mode == 2 ? 3 : 2 + k, k, t.images,
+               images_done ? 100.0 * t.images / images_done : 0.0);
         printf("   Total GPU time:        %.2f ms\n", tot);
         printf("   - Transfer IN:         %.2f ms (%.1f%%)\n", t.in_ms, tot > 0 ? t.in_ms / tot * 100 : 0.0);
         printf("   - Kernel execution:    %.2f ms (%.1f%%)\n", t.kernel_ms, tot > 0 ? t.kernel_ms / tot * 100 : 0.0);
@@ -321,13 +368,13 @@ int main(int argc, char **argv)
             if (workers[k].t.total() > workers[slow].t.total()) slow = k;
         }
         const double tf = workers[fast].t.total(), ts = workers[slow].t.total();
-        printf("4. DEVICE COMPARISON\n");
+        printf("%d. DEVICE COMPARISON\n", sec_base);
         printf("   GPU %d is %.2fx FASTER than GPU %d\n", fast, tf > 0 ? ts / tf : 1.0, slow);
         printf("   slowest/fastest time ratio: %.2f\n\n", tf > 0 ? ts / tf : 1.0);
-        printf("5. WORKLOAD BALANCE\n");
+        printf("%d. WORKLOAD BALANCE\n", sec_base + 1);
         printf("   Workload imbalance: %.1f%%\n", ts > 0 ? fabs(ts - tf) / ts * 100.0 : 0.0);
         printf("   GPU %d is the BOTTLENECK (%.2f ms slower)\n\n", slow, ts - tf);
-        printf("6. BOTTLENECK IDENTIFICATION\n");
+        printf("%d. BOTTLENECK IDENTIFICATION\n", sec_base + 2);
         for (int k = 0; k < G; k++) {
             const DeviceTimes &t = workers[k].t;
             if (t.images == 0) continue;
@@ -340,7 +387,7 @@ int main(int argc, char **argv)
     }
     printf("\n");
 
-    printf("7. THROUGHPUT\n");
+    printf("%d. THROUGHPUT\n", sec_base + 3);
     const double secs = time_total_processing / 1000.0;
     printf("   Overall throughput: %.2f Megapixels/sec\n", (double)images_done * width * height / secs / 1e6);
     printf("   Images per second: %.2f\n", images_done / secs);
@@ -358,7 +405,7 @@ int main(int argc, char **argv)
     printf("\n=========================================\n\n");
 
     if (G > 1) {
-        printf("8. OPTIMAL RATIO RECOMMENDATION\n");
+        printf("%d. OPTIMAL RATIO RECOMMENDATION\n", sec_base + 4);
         printf("   Based on measured performance:\n");
         double inv_sum = 0;
         for (int k = 0; k < G; k++)
@@ -366,11 +413,22 @@ int main(int argc, char **argv)
         for (int k = 0; k < G; k++) {
             const DeviceTimes &t = workers[k].t;
             if (!t.images) continue;
-            printf("   GPU %d: %.5f ms/image -> recommended share %.1f%%\n", k, t.total() / t.images,
-                   (t.images / t.total()) / inv_sum * 100);
+            printf("   GPU %d: %.5f ms/image -> recommended share %.1f%%, share taken %.1f%%\n", k, t.total() / t.images,
+                   (t.images / t.total()) / inv_sum * 100, images_done ? 100.0 * t.images / images_done : 0.0);
         }
-        printf("   Run with: ./heterogeneous_blur both %.3f   (shares are even by construction; ratio kept for compatibility)\n\n",
-               gpu_ratio);
+        if (!opt.resident) {
+            // how evenly the GPUs finished: wall-clock time of each GPU's last result relative to the slowest
+            double last = 0, first = 1e300;
+            for (auto &w : workers) {
+                last = std::max(last, w.t.busy_until_ms);
+                first = std::min(first, w.t.busy_until_ms);
+            }
+            printf("   Finish-time spread over GPUs: %.2f ms (%.1f%% of the run; %s)\n", last - first,
+                   time_total_processing > 0 ? (last - first) / time_total_processing * 100 : 0.0,
+                   stealing ? "work taken dynamically from a shared counter" : "fixed even partition of every batch");
+        }
+        printf("   Run with: ./heterogeneous_blur both %.3f   (ratio kept for compatibility; shares are %s)\n\n", gpu_ratio,
+               stealing ? "measured, not set" : "even by construction");
     }
 
     if (!opt.save.empty()) {

@@ -85,5 +85,47 @@ def test_split_image_blur_cli(photo, extra):
     text = run([os.path.join(BIN, "split_image_blur"), "0.837", "35", "--images", "80", "--input", path, "--save", out_path,
                 "--quiet", "--checksum"] + extra, d)
     assert "SPLIT-IMAGE CONFIGURATION" in text and "split row 39" in text  # split_image_blur.c:144 known answer
-    assert f"Row bands over {g} GPU(s)" in text and "9. OPTIMAL RATIO RECOMMENDATION" in text
+    assert f"Row bands over {g} GPU(s)" in text and f"{max(g, 2) + 7}. OPTIMAL RATIO RECOMMENDATION" in text
     assert np.array_equal(read_ppm(out_path), want)
+
+
+def _field(text, label):
+    for line in text.splitlines():
+        if label in line:
+            return line.split(label, 1)[1].strip()
+    raise AssertionError(f"{label!r} not in output")
+
+
+@pytest.mark.parametrize("extra", [[], ["--static-split"]], ids=["work-stealing", "static-split"])
+def test_heterogeneous_blur_cli_four_workers(photo, extra):
+    """Approach 1 over 4 GPU workers (on a box with fewer GPUs the workers share devices: --oversubscribe).  By default the
+    workers TAKE groups of batches from a shared counter (dynamic scheduling instead of the reference's
+    hand-tuned ratio, heterogeneous_blur.c:713-722); every image is processed exactly once either way."""
+    d, path, img, want = photo
+    out_path = os.path.join(d, f"a1_four_{len(extra)}.ppm")
+    text = run([os.path.join(BIN, "heterogeneous_blur"), "both", "0.5", "5", "--images", "1003", "--gpus", "4", "--oversubscribe",
+                "--input", path, "--save", out_path, "--quiet"] + extra, d)
+    assert "Total images processed: 1003" in text
+    assert "6. DEVICE COMPARISON" in text and "9. THROUGHPUT" in text and "10. OPTIMAL RATIO RECOMMENDATION" in text
+    shares = [int(line.split("processed")[1].split("images")[0]) for line in text.splitlines() if "DEVICE (processed" in line]
+    assert sum(shares) == 1003 and len(shares) >= 1
+    if extra:
+        assert len(shares) == 4 and max(shares) - min(shares) <= 201   # even shares of every batch of 5 (1 or 2 images)
+    assert np.array_equal(read_ppm(out_path), want)
+
+
+def test_split_image_blur_cli_eight_bands_stress(photo):
+    """8 row bands x 200 batches with a ring of only 2 slots: every batch, each band's kernel waits for its neighbours'
+    uploads and each upload waits for the neighbours' previous kernels THROUGH THE OTHER THREAD'S CONTEXT
+    (b200blur_enqueue_wait_peer) while that thread keeps creating events (round-1 race: the event pool reallocated under
+    the reader).  All outputs (checksum) must equal the host-halo scheme's, and image 0 the oracle's."""
+    d, path, img, want = photo
+    sums = []
+    for i, extra in enumerate([[], ["--host-halo"]]):
+        out_path = os.path.join(d, f"a2_stress_{i}.ppm")
+        text = run([os.path.join(BIN, "split_image_blur"), "0.5", "1", "--images", "200", "--gpus", "8", "--oversubscribe",
+                    "--ring", "2", "--fuse", "1", "--input", path, "--save", out_path, "--quiet", "--checksum"] + extra, d)
+        assert "Row bands over 8 GPU(s)" in text and "Total images processed: 200" in text
+        assert np.array_equal(read_ppm(out_path), want)
+        sums.append(_field(text, "Output checksum"))
+    assert sums[0] == sums[1]

@@ -28,6 +28,7 @@ def ctx(request):
     oracle.build()
     c = b200blur.Context(0, 4)
     c.set_kernel_variant(request.param)
+    c.variant = request.param
     yield c
     c.close()
 
@@ -390,8 +391,10 @@ def test_profiling_events_and_2d_transfers(ctx):
     assert_same(out, oracle.c_blur_batch(x)[:, 1:h - 1])
 
 
-@pytest.mark.parametrize("batch_size,coalesce", [(35, True), (35, False), (1, False), (500, False), (5000, True)])
+@pytest.mark.parametrize("batch_size,coalesce", [(35, 1), (35, 0), (35, 2), (1, 0), (1, 2), (500, 0), (5000, 1), (5000, 0)])
 def test_run_resident_matches_oracle(ctx, batch_size, coalesce):
+    """coalesce: 1 = batches fused into one launch, 0 = one work descriptor per batch through the feed kernel (one
+    launch per call), 2 = one kernel launch per batch."""
     import torch
     n, h, w, c = 143, 240, 320, 3
     x = synth(17, n, h, w, c)
@@ -401,7 +404,9 @@ def test_run_resident_matches_oracle(ctx, batch_size, coalesce):
     before = ctx.launch_count
     st = ctx.run_resident(d_in, d_out, w, h, c, n, batch_size, coalesce)
     torch.cuda.synchronize()
-    want_launches = 1 if coalesce else (n + batch_size - 1) // batch_size
+    n_batches = (n + batch_size - 1) // batch_size
+    feed = coalesce == 0 and n_batches > 1 and ctx.variant == 0   # the feed kernel is the streamed kernel
+    want_launches = 1 if (coalesce == 1 or feed) else n_batches
     assert st.launches == want_launches and ctx.launch_count - before == want_launches
     assert st.images == n and st.kernel_ms > 0
     assert_same(d_out.cpu().numpy(), oracle.c_blur_batch(x, integer=True))
