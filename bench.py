@@ -70,6 +70,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 5))")
+    ap.add_argument("--e2e-phased", type=int, default=-1, help="end-to-end pipeline with one transfer direction per GPU at a time: 1/0 (default: 1 when >= 4 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip configs / a2_split / sustained (value, e2e, roofline only)")
     ap.add_argument("--sustained-seconds", type=float, default=2.5)
@@ -322,7 +323,7 @@ def oracle_sample_check(d_in, d_out, n, k=16):
 
 
 # ------------------------------------------------------------------------------------- host-link roofline (all ranks)
-def measure_link(env, ctx, h_in, h_out, d_in, d_out, nbytes, reps=3, chunk=64 << 20):
+def measure_link(env, ctx, h_in, h_out, d_in, d_out, nbytes, reps=3, chunk=64 << 20, only=None):
     """Every rank moves its pinned input host->device on queue 0 and its output device->host on queue 2 AT THE SAME TIME
     as every other rank, in 64 MB linear copies, no kernel: the ceiling the end-to-end pipeline can reach on this box
     with N GPUs active.  -> best-of-reps (max over ranks per rep) GB/s each way per GPU."""
@@ -333,8 +334,10 @@ def measure_link(env, ctx, h_in, h_out, d_in, d_out, nbytes, reps=3, chunk=64 <<
         ctx.enqueue_wait(2, e0)
         for off in range(0, nbytes, chunk):
             m = min(chunk, nbytes - off)
-            ctx.enqueue_write(0, d_in + off, h_in + off, m)
-            ctx.enqueue_read(2, h_out + off, d_out + off, m)
+            if only != "d2h":
+                ctx.enqueue_write(0, d_in + off, h_in + off, m)
+            if only != "h2d":
+                ctx.enqueue_read(2, h_out + off, d_out + off, m)
         e2 = ctx.enqueue_marker(2)
         ctx.enqueue_wait(0, e2)
         e1 = ctx.enqueue_marker(0)
@@ -493,6 +496,10 @@ def run_b200_arm(args) -> None:
         del scratch
 
     # ---- end to end through the C-ABI stream engine with pinned host buffers
+    # With >= 4 GPUs on one host fabric the pipeline runs one transfer direction per GPU at a time (B200BLUR_E2E_PHASED,
+    # see b200blur_run_host): the fabric carries more with fewer concurrent flows.  --e2e-phased 0/1 overrides.
+    phased = (world >= 4) if args.e2e_phased < 0 else bool(args.e2e_phased)
+    os.environ["B200BLUR_E2E_PHASED"] = "1" if phased else "0"
     e2e_steps = args.e2e_steps or max(1, min(args.steps, 5))
     h_in = torch.empty((N_IMAGES, HEIGHT, WIDTH, CHANNELS), dtype=torch.uint8).pin_memory()
     h_in.copy_(d_in)
@@ -523,6 +530,11 @@ def run_b200_arm(args) -> None:
     # host-link roofline for the e2e number at THIS N: all ranks, both directions at once, same pinned buffers, no kernel
     link_gbps = measure_link(env, ctx, h_in.data_ptr(), h_out.data_ptr(), d_in.data_ptr(), d_out.data_ptr(),
                              N_IMAGES * IMAGE_BYTES)
+    # ... and with half the GPUs uploading while the other half download (what the phased pipeline approaches)
+    link_split = None
+    if world >= 2:
+        link_split = measure_link(env, ctx, h_in.data_ptr(), h_out.data_ptr(), d_in.data_ptr(), d_out.data_ptr(),
+                                  N_IMAGES * IMAGE_BYTES, only="h2d" if rank % 2 == 0 else "d2h")
     del h_in, h_out, d_check
 
     # ---- sustained: >= ~2 s of back-to-back passes, clocks and power sampled during the region
@@ -553,8 +565,8 @@ def run_b200_arm(args) -> None:
         a2_split = run_a2(env, ctx, 5000, 256, 256, max(args.steps, 50), max(args.warmup, 5),   # (a step is only 40-160 us)
                           "A2 split-image: 5000x 256x256 RGB, row bands + 1-row halo over NVLink (BASELINE.json configs[2])")
         torch.cuda.empty_cache()
-        a2_large = run_a2(env, ctx, 16, 8192, 8192, max(3, args.steps // 2), 2,
-                          "A2 large frames: 16 of the 1000x 8192x8192 RGB frames, row bands over NVLink (BASELINE.json configs[4])",
+        a2_large = run_a2(env, ctx, 32, 8192, 8192, max(3, args.steps // 2), 2,
+                          "A2 large frames: 32 of the 1000x 8192x8192 RGB frames, row bands over NVLink (BASELINE.json configs[4])",
                           oracle_images=1)
         total_launches += a2_split["gpu_launches"] + a2_large["gpu_launches"]
 
@@ -601,7 +613,12 @@ def run_b200_arm(args) -> None:
                     "link_roofline": {
                         "bound": f"host link with all {world} GPU(s) copying both directions at once (same pinned buffers, 64 MB linear copies, no kernel; max over ranks)",
                         "peak_GBps_each_way_per_gpu": link_gbps, "aggregate_GBps_each_way": link_gbps * world,
-                        "frac": e2e_gbps / link_gbps},
+                        "frac": e2e_gbps / link_gbps,
+                        "split_directions": None if link_split is None else {
+                            "bound": "even ranks upload only, odd ranks download only (one direction per GPU)",
+                            "aggregate_GBps_each_way": link_split * (world // 2 if world > 1 else 1),
+                            "note": "GB/s of a direction = bytes moved by the ranks of that direction / time of the slowest rank"}},
+                    "pipeline_mode": "one direction per GPU at a time (B200BLUR_E2E_PHASED=1)" if phased else "uploads and downloads overlap on every GPU",
                     "api": "b200blur_run_host (pinned host buffers, 3 queues, 4-slot device ring, batches fused into ~64 MB transfer chunks)"},
             "configs": configs, "a2_split": a2_split, "a2_large": a2_large,
             "gpu_launches": int(total_launches),
@@ -678,7 +695,7 @@ def run_split_only(args) -> None:
     import b200blur
     env = Env()
     ctx = b200blur.Context(env.local_rank, 4)
-    r = run_a2(env, ctx, 5000, 256, 256, args.steps, args.warmup,
+    r = run_a2(env, ctx, 5000, int(os.environ.get("A2_HEIGHT", "256")), 256, args.steps, args.warmup,
                "A2 split-image: 5000x 256x256 RGB, row bands + 1-row halo over NVLink (BASELINE.json configs[2])")
     if env.rank == 0:
         peak, note = load_peak()

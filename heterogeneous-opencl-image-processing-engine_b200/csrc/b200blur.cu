@@ -292,7 +292,7 @@ constexpr StreamCfg make_cfg()
 
 // {rows per slot, slots}; index 0 is the default (B200BLUR_V2_CFG selects another for tuning runs)
 // (round-1 sweep over {8,4} {8,3} {4,3} {4,4} {4,6} {16,2} {8,2}: all within 3 % once work is handed out dynamically)
-const StreamCfg kStreamCfgs[] = {make_cfg<8, 4>(), make_cfg<8, 3>()};
+const StreamCfg kStreamCfgs[] = {make_cfg<8, 4>(), make_cfg<8, 3>(), make_cfg<8, 6>()};
 constexpr int kNumStreamCfgs = sizeof(kStreamCfgs) / sizeof(kStreamCfgs[0]);
 
 // Whether the streamed (variant 2) kernel can run this launch: rows wide enough for bulk copies to pay.
@@ -1580,8 +1580,8 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
     // per-chunk event/dependency gaps cap the link at 33 GB/s each way; at 64 MB it reaches the 45 GB/s this host link
     // sustains with both directions active -- tools/linkbench.py, tools/e2e.py.)  B200BLUR_E2E_CHUNK_MB overrides the
     // target (0 = exactly one batch per chunk, the reference's granularity); B200BLUR_RING overrides the ring depth.
-    static const int env_ring = getenv("B200BLUR_RING") ? atoi(getenv("B200BLUR_RING")) : 0;
-    static const int env_chunk_mb = getenv("B200BLUR_E2E_CHUNK_MB") ? atoi(getenv("B200BLUR_E2E_CHUNK_MB")) : 64;
+    const int env_ring = getenv("B200BLUR_RING") ? atoi(getenv("B200BLUR_RING")) : 0;
+    const int env_chunk_mb = getenv("B200BLUR_E2E_CHUNK_MB") ? atoi(getenv("B200BLUR_E2E_CHUNK_MB")) : 64;
     const int n_slots = env_ring > 1 ? env_ring : 4;
     if (env_chunk_mb > 0 && image_bytes > 0) {
         const double target = (double)env_chunk_mb * 1024 * 1024;
@@ -1625,47 +1625,82 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
         return B200BLUR_OK;
     };
 
-    for (int64_t ci = 0; ci < n_chunks; ci++) {
+    // One chunk's three stages.  `phase`: 0 = all three, 1 = upload + kernel only, 2 = download only.
+    auto issue = [&](int64_t ci, int phase) -> int {
         b200blur_ctx::Slot &s = ctx->ring[ci % n_slots];
-        if (ci >= n_slots)
-            if (int rc = harvest(s)) return rc;  // slot's previous chunk fully drained (also frees d_in/d_out)
         const int64_t i0 = ci * batch_size;
         const int64_t n = (n_images - i0 < batch_size) ? n_images - i0 : batch_size;
         const size_t bytes = (size_t)n * image_bytes;
         const uint8_t *src = static_cast<const uint8_t *>(h_in) + (size_t)i0 * image_bytes;
         uint8_t *dst = static_cast<uint8_t *>(h_out) + (size_t)i0 * image_bytes;
-        // H2D
-        CU_TRY(cudaEventRecord(s.ev[0], q_in));
-        if (bytes) CU_TRY(cudaMemcpyAsync(repitch ? s.t_in : s.d_in, src, bytes, cudaMemcpyHostToDevice, q_in));
-        CU_TRY(cudaEventRecord(s.ev[1], q_in));
-        // blur
-        CU_TRY(cudaStreamWaitEvent(q_k, s.ev[1], 0));
-        CU_TRY(cudaEventRecord(s.ev[2], q_k));
-        b200blur_launch l;
-        if (int rc = b200blur_launch_rows_pitched(&l, s.d_in, s.d_out, width, height, channels, 0, height, n,
-                                                  dev_image_bytes, dev_image_bytes, repitch ? dev_pitch : 0,
-                                                  repitch ? dev_pitch : 0))
-            return rc;
-        if (repitch && bytes) {
-            launch_repitch_in(ctx, q_k, s.t_in, s.d_in, n * (long long)height, (int)row_bytes, (int)dev_pitch);
-            launches++;
+        if (phase != 2) {
+            // H2D
+            CU_TRY(cudaEventRecord(s.ev[0], q_in));
+            if (bytes) CU_TRY(cudaMemcpyAsync(repitch ? s.t_in : s.d_in, src, bytes, cudaMemcpyHostToDevice, q_in));
+            CU_TRY(cudaEventRecord(s.ev[1], q_in));
+            // blur
+            CU_TRY(cudaStreamWaitEvent(q_k, s.ev[1], 0));
+            CU_TRY(cudaEventRecord(s.ev[2], q_k));
+            b200blur_launch l;
+            if (int rc = b200blur_launch_rows_pitched(&l, s.d_in, s.d_out, width, height, channels, 0, height, n,
+                                                      dev_image_bytes, dev_image_bytes, repitch ? dev_pitch : 0,
+                                                      repitch ? dev_pitch : 0))
+                return rc;
+            if (repitch && bytes) {
+                launch_repitch_in(ctx, q_k, s.t_in, s.d_in, n * (long long)height, (int)row_bytes, (int)dev_pitch);
+                launches++;
+            }
+            int nk;
+            if (int rc = do_launch(ctx, 1, &l, &nk)) return rc;
+            launches += nk;
+            if (repitch && bytes) {
+                launch_repitch_out(ctx, q_k, s.d_out, s.t_out, 0, n * (long long)height, (int)row_bytes, (int)dev_pitch);
+                launches++;
+            }
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaEventRecord(s.ev[3], q_k));
         }
-        int nk;
-        if (int rc = do_launch(ctx, 1, &l, &nk)) return rc;
-        launches += nk;
-        if (repitch && bytes) {
-            launch_repitch_out(ctx, q_k, s.d_out, s.t_out, 0, n * (long long)height, (int)row_bytes, (int)dev_pitch);
-            launches++;
+        if (phase != 1) {
+            // D2H
+            CU_TRY(cudaStreamWaitEvent(q_out, s.ev[3], 0));
+            CU_TRY(cudaEventRecord(s.ev[4], q_out));
+            if (bytes) CU_TRY(cudaMemcpyAsync(dst, repitch ? s.t_out : s.d_out, bytes, cudaMemcpyDeviceToHost, q_out));
+            CU_TRY(cudaEventRecord(s.ev[5], q_out));
         }
-        CU_TRY(cudaGetLastError());
-        CU_TRY(cudaEventRecord(s.ev[3], q_k));
-        // D2H
-        CU_TRY(cudaStreamWaitEvent(q_out, s.ev[3], 0));
-        CU_TRY(cudaEventRecord(s.ev[4], q_out));
-        if (bytes) CU_TRY(cudaMemcpyAsync(dst, repitch ? s.t_out : s.d_out, bytes, cudaMemcpyDeviceToHost, q_out));
-        CU_TRY(cudaEventRecord(s.ev[5], q_out));
+        return B200BLUR_OK;
+    };
+
+    // B200BLUR_E2E_PHASED=1: one transfer direction per GPU at a time.  The chunks move in waves of one ring: all uploads
+    // (+ kernels) of a wave, then all its downloads, then the next wave's uploads.  A single GPU loses by it (its link is
+    // full duplex: 46 GB/s each way at once, 55 one way), but when many GPUs share one host fabric the fabric carries
+    // more with fewer flows per link -- measured on an 8-GPU box of this pool (tools/linkbench_multi.py,
+    // profiles/r02_linkbench_n8.txt): 64 GB/s each way with all 16 flows at once, 75 GB/s each way with half the GPUs
+    // uploading while the other half download.  Processes are not synchronised with each other; their waves interleave.
+    const char *env_phased = getenv("B200BLUR_E2E_PHASED");
+    const bool phased = env_phased && atoi(env_phased) != 0;
+    if (!phased) {
+        for (int64_t ci = 0; ci < n_chunks; ci++) {
+            if (ci >= n_slots)
+                if (int rc = harvest(ctx->ring[ci % n_slots])) return rc;  // slot's previous chunk fully drained (also frees d_in/d_out)
+            if (int rc = issue(ci, 0)) return rc;
+        }
+    } else {
+        for (int64_t w0 = 0; w0 < n_chunks; w0 += n_slots) {
+            const int64_t w1 = (w0 + n_slots < n_chunks) ? w0 + n_slots : n_chunks;
+            if (w0 > 0) {
+                for (int64_t ci = w0 - n_slots; ci < w0; ci++)
+                    if (int rc = harvest(ctx->ring[ci % n_slots])) return rc;   // the previous wave's downloads are done
+            }
+            for (int64_t ci = w0; ci < w1; ci++)
+                if (int rc = issue(ci, 1)) return rc;
+            // downloads start when the wave's last upload has finished
+            CU_TRY(cudaStreamWaitEvent(q_out, ctx->ring[(w1 - 1) % n_slots].ev[1], 0));
+            for (int64_t ci = w0; ci < w1; ci++)
+                if (int rc = issue(ci, 2)) return rc;
+        }
     }
-    const int64_t first_pending = n_chunks > n_slots ? n_chunks - n_slots : 0;
+    int64_t first_pending = n_chunks > n_slots ? n_chunks - n_slots : 0;
+    if (phased && n_chunks > 0) first_pending = (n_chunks - 1) / n_slots * n_slots;   // earlier waves were harvested
     for (int64_t ci = first_pending; ci < n_chunks; ci++)
         if (int rc = harvest(ctx->ring[ci % n_slots])) return rc;
     CU_TRY(cudaStreamSynchronize(q_out));

@@ -432,6 +432,21 @@ def test_run_host_pipeline_matches_oracle(ctx, batch_size):
     assert_same(out2, h_out.numpy())
 
 
+@pytest.mark.parametrize("n,batch_size,chunk_mb", [(300, 35, 4), (41, 1, 1), (97, 8, 0)])
+def test_run_host_one_direction_at_a_time(ctx, monkeypatch, n, batch_size, chunk_mb):
+    """B200BLUR_E2E_PHASED=1: the chunks move in waves (all uploads of a ring, then all its downloads) so that only one
+    transfer direction is active per GPU -- the mode for boxes where many GPUs share one host fabric.  Same results; small
+    transfer chunks so that several waves (and a short last one) happen."""
+    h, w, c = 64, 320, 3
+    x = synth(n + batch_size, n, h, w, c)
+    monkeypatch.setenv("B200BLUR_E2E_PHASED", "1")
+    monkeypatch.setenv("B200BLUR_E2E_CHUNK_MB", str(chunk_mb))
+    out = np.zeros_like(x)
+    st = ctx.run_host(x, out, w, h, c, n, batch_size)
+    assert st.images == n and st.h2d_ms > 0 and st.d2h_ms > 0
+    assert_same(out, oracle.c_blur_batch(x, integer=True))
+
+
 def test_full_size_stream_properties(ctx):
     """BASELINE configs[1] at full size: 5000 x 320x240.  (a) the reference's own stream -- 5000 replicas of one image
     (heterogeneous_blur.c:440-442) -- must give 5000 copies of the oracle's output; (b) distinct random images:
