@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "b200blur.h"
+#include "jpeg_decode.hpp"
 
 // cl_error(): print "<code> - <message>" and exit(-1), the reference's only error path for device calls.
 inline void blur_check(int code, const char *what)
@@ -153,12 +154,44 @@ inline int parse_extra(int argc, char **argv, int first, ExtraOptions &o)
     return 0;
 }
 
-// The reference's LOAD ORIGINAL IMAGE section (heterogeneous_blur.c:104-137) without CImg/libjpeg.
+// The reference's LOAD ORIGINAL IMAGE section (heterogeneous_blur.c:104-137) without CImg/libjpeg: --input takes a
+// .jpg/.jpeg (decoded like libjpeg does by default, host/jpeg_decode.hpp) or a binary .ppm; with no --input the
+// reference's hard-coded ./image_320x240.jpg (heterogeneous_blur.c:43) is used if it is in the working directory, then
+// ./image_320x240.ppm, then a synthetic image.
+inline bool is_jpeg_file(const char *path)
+{
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return false;
+    unsigned char m[2] = {0, 0};
+    const bool ok = fread(m, 1, 2, fp) == 2 && m[0] == 0xFF && m[1] == 0xD8;
+    fclose(fp);
+    return ok;
+}
+
+inline bool load_image_file(const char *path, Image &img, std::string &err)
+{
+    if (is_jpeg_file(path)) {
+        std::vector<uint8_t> px;
+        int w, h, c;
+        err = jpegdec::load_jpeg(path, w, h, c, px);
+        if (!err.empty()) return false;
+        img.width = w; img.height = h; img.channels = c;
+        img.data.assign(px.begin(), px.end());
+        return true;
+    }
+    if (load_ppm(path, img)) return true;
+    err = "not a readable JPEG or binary PPM (P6, maxval 255) file";
+    return false;
+}
+
 inline void load_source_image(const ExtraOptions &o, Image &img, std::string &name)
 {
+    std::string err;
     if (!o.input.empty()) {
-        if (!load_ppm(o.input.c_str(), img)) { printf("Error: cannot read PPM file %s\n", o.input.c_str()); exit(-1); }
+        if (!load_image_file(o.input.c_str(), img, err)) { printf("Error: cannot read image file %s (%s)\n", o.input.c_str(), err.c_str()); exit(-1); }
         name = o.input;
+    } else if (o.width == 320 && o.height == 240 && load_image_file("./image_320x240.jpg", img, err)) {
+        name = "./image_320x240.jpg";
     } else if (o.width == 320 && o.height == 240 && load_ppm("./image_320x240.ppm", img)) {
         name = "./image_320x240.ppm";
     } else {

@@ -129,3 +129,18 @@ def test_split_image_blur_cli_eight_bands_stress(photo):
         assert np.array_equal(read_ppm(out_path), want)
         sums.append(_field(text, "Output checksum"))
     assert sums[0] == sums[1]
+
+
+@pytest.mark.parametrize("name", ["420_q30_96x80.jpg", "420_photo_crop_80x50.jpg", "420_q75_odd_101x67.jpg"])
+def test_cli_blurs_a_jpeg_input(tmp_path, name):
+    """Ingest -> hot path: the CLI decodes a .jpg itself (host/jpeg_decode.hpp, byte-identical to libjpeg) and its saved
+    output equals the oracle's blur of those decoded pixels."""
+    src = os.path.join(ROOT, "tests", "golden", "jpeg", name)
+    ppm = os.path.join(tmp_path, "decoded.ppm")
+    subprocess.run([os.path.join(BIN, "jpeg2ppm"), src, ppm], check=True, capture_output=True)
+    want = oracle.c_blur(read_ppm(ppm))
+    out_path = os.path.join(tmp_path, "out.ppm")
+    text = run([os.path.join(BIN, "heterogeneous_blur"), "gpu", "0.5", "7", "--images", "50", "--input", src, "--save", out_path,
+                "--quiet"], str(tmp_path))
+    assert "Total images processed: 50" in text
+    assert np.array_equal(read_ppm(out_path), want)
