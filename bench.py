@@ -70,7 +70,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 5))")
-    ap.add_argument("--e2e-phased", type=int, default=-1, help="end-to-end pipeline with one transfer direction per GPU at a time: 1/0 (default: 1 when >= 4 GPUs)")
+    ap.add_argument("--e2e-phased", type=int, default=-1, help="end-to-end pipeline with one transfer direction per GPU at a time: 1/0 (default 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip configs / a2_split / sustained (value, e2e, roofline only)")
     ap.add_argument("--sustained-seconds", type=float, default=2.5)
@@ -496,9 +496,11 @@ def run_b200_arm(args) -> None:
         del scratch
 
     # ---- end to end through the C-ABI stream engine with pinned host buffers
-    # With >= 4 GPUs on one host fabric the pipeline runs one transfer direction per GPU at a time (B200BLUR_E2E_PHASED,
-    # see b200blur_run_host): the fabric carries more with fewer concurrent flows.  --e2e-phased 0/1 overrides.
-    phased = (world >= 4) if args.e2e_phased < 0 else bool(args.e2e_phased)
+    # --e2e-phased 1 runs the pipeline with one transfer direction per GPU at a time (B200BLUR_E2E_PHASED, see
+    # b200blur_run_host).  Off by default: with unsynchronised ranks it measured SLOWER on this pool's 8-GPU box (275.8 k
+    # vs 287.6 k images/s at N=8, 199.0 k vs 222.7 k at N=4; profiles/r02_e2e_phased.md) although the fabric itself carries
+    # 16 % more when half the GPUs only upload and half only download (e2e.link_roofline.split_directions).
+    phased = bool(args.e2e_phased) if args.e2e_phased >= 0 else False
     os.environ["B200BLUR_E2E_PHASED"] = "1" if phased else "0"
     e2e_steps = args.e2e_steps or max(1, min(args.steps, 5))
     h_in = torch.empty((N_IMAGES, HEIGHT, WIDTH, CHANNELS), dtype=torch.uint8).pin_memory()
