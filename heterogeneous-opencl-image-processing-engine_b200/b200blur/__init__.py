@@ -18,6 +18,7 @@ from .lib import (  # noqa: F401
     lib_path,
     load,
     partition,
+    plan_groups,
     plan_row_edge,
     ratio_split_images,
     ratio_split_row,

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "b200blur_enqueue_blur": (c_int, [c_void_p, c_int, POINTER(Launch), POINTER(c_int32)]),
     "b200blur_launch_is_vectorised": (c_int, [POINTER(Launch)]),
     "b200blur_plan_row_edge": (c_int, [c_int, c_int, POINTER(ctypes.c_uint32)]),
+    "b200blur_plan_groups": (c_int, [c_int, c_int, c_int, c_int64, c_size_t, c_int, c_int, POINTER(c_int64)]),
     "b200blur_set_kernel_variant": (c_int, [c_void_p, c_int]),
     "b200blur_ctx_launch_count": (c_int64, [c_void_p]),
     "b200blur_partition": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
@@ -186,6 +187,16 @@ def plan_row_edge(row_bytes: int, channels: int):
     _check(load().b200blur_plan_row_edge(row_bytes, channels, out))
     return {"chunks": out[0], "edge_general": bool(out[1]), "edge_prev": bool(out[2]),
             "sel_last": [out[3 + m] for m in range(6)], "sel_prev": out[9]}
+
+
+def plan_groups(width: int, rows: int, channels: int, n_images: int, row_pitch: int = 0, resident_ctas: int = 444,
+                feed: bool = False):
+    """Host-side work plan of the streamed kernel (b200blur_plan_groups) -> dict; needs no GPU."""
+    out = (c_int64 * 16)()
+    _check(load().b200blur_plan_groups(width, rows, channels, n_images, row_pitch, resident_ctas, int(feed), out))
+    keys = ("cpr", "cb", "ncb", "ipc", "seg", "nseg", "seg_fine", "nseg_fine", "img_blocks", "ib_coarse", "g_coarse", "n_groups",
+            "margin", "block", "smem", "edge_general")
+    return dict(zip(keys, (int(v) for v in out)))
 
 
 def _ptr(p) -> int:

@@ -341,7 +341,8 @@ struct StreamPlan {
 };
 
 // Plans the streamed kernel for band geometry `p` (p.n_images images per launch, or -- feed -- per batch at most).
-int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, StreamPlan &plan)
+// `slots_override` > 0: plan for that many resident CTAs without asking the CUDA runtime (host-side introspection).
+int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, StreamPlan &plan, long long slots_override = 0)
 {
     b200blur::StreamParams &sp = plan.sp;
     memset(&sp, 0, sizeof sp);
@@ -391,7 +392,7 @@ int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, Str
     plan.block = threads + (feed ? 64 : 32);  // + the producer warp (+ the accountant warp of a feed)
     if (plan.smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", plan.smem);
     plan.fn = feed ? cfg.fn_feed[p.channels - 1] : sp.edge_general ? cfg.fn_edge[p.channels - 1] : cfg.fn[p.channels - 1];
-    int per_sm = 0;
+    int per_sm = slots_override > 0 ? 1 : 0;
     for (auto &ki : ctx->kernel_info)
         if (ki.fn == (const void *)plan.fn && ki.block == plan.block && ki.smem == plan.smem) per_sm = ki.per_sm;
     if (per_sm == 0) {
@@ -402,7 +403,7 @@ int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, Str
         ctx->kernel_info.push_back({(const void *)plan.fn, plan.block, plan.smem, per_sm});
     }
     if (ctx->v2_ctas_per_sm > 0 && per_sm > ctx->v2_ctas_per_sm) per_sm = ctx->v2_ctas_per_sm;
-    plan.slots = (long long)ctx->sm_count * per_sm;
+    plan.slots = slots_override > 0 ? slots_override : (long long)ctx->sm_count * per_sm;
     sp.img_blocks = (p.n_images + sp.ipc - 1) / sp.ipc;
     // Work unit = `seg` output rows of `ipc` images (or of one column block): ~48 KB in + 48 KB out for whole
     // rows, ~128 KB for column blocks; the band is cut into equal segments of about that size.
@@ -1118,6 +1119,35 @@ int b200blur_plan_row_edge(int row_bytes, int channels, uint32_t out[10])
     out[2] = (uint32_t)sp.edge_prev;
     for (int m = 0; m < 6; m++) out[3 + m] = sp.sel_last[m];
     out[9] = sp.sel_prev;
+    return B200BLUR_OK;
+}
+
+int b200blur_plan_groups(int width, int rows, int channels, int64_t n_images, size_t row_pitch, int resident_ctas, int feed,
+                         int64_t out[16])
+{
+    if (!out || width < 1 || rows < 1 || channels < 1 || channels > 4 || n_images < 1 || resident_ctas < 1)
+        return fail(B200BLUR_ERR_INVALID, "bad plan request");
+    const size_t row_bytes = (size_t)width * channels;
+    if (row_pitch == 0) row_pitch = row_bytes;
+    if (row_pitch % 16 || row_pitch < row_bytes || row_pitch > 0x7fffffffULL || row_bytes < 256)
+        return fail(B200BLUR_ERR_INVALID, "the streamed kernel needs rows of >= 256 bytes and a row pitch that is a multiple of 16");
+    b200blur_ctx tmp;   // knobs at their defaults; no device is touched
+    tmp.sm_count = 148;
+    b200blur::BandParams p;
+    memset(&p, 0, sizeof p);
+    p.in_stride = p.out_stride = row_pitch * (size_t)rows;
+    p.row_bytes = (int)row_bytes;
+    p.pitch = p.out_pitch = (int)row_pitch;
+    p.rows = rows;
+    p.width = width;
+    p.channels = channels;
+    p.n_images = n_images;
+    StreamPlan plan;
+    if (int rc = plan_stream(&tmp, p, feed != 0, plan, resident_ctas)) return rc;
+    const b200blur::StreamParams &sp = plan.sp;
+    const int64_t v[16] = {sp.cpr, sp.cb, sp.ncb, sp.ipc, sp.seg, sp.nseg, sp.seg_fine, sp.nseg_fine, sp.img_blocks, sp.ib_coarse,
+                           sp.g_coarse, sp.n_groups, sp.margin, plan.block, (int64_t)plan.smem, sp.edge_general};
+    memcpy(out, v, sizeof v);
     return B200BLUR_OK;
 }
 

@@ -190,6 +190,15 @@ B200BLUR_API int b200blur_set_kernel_variant(b200blur_ctx *ctx, int variant);
  * out[2] = 1 when the chunk before the last needs its right-neighbour word patched too, out[3..8] = PRMT selectors
  * for the six window words {wl, w0..w3, wr} of the last chunk, out[9] = selector for the wr word of the chunk before. */
 B200BLUR_API int b200blur_plan_row_edge(int row_bytes, int channels, uint32_t out[10]);
+/* Host-side work plan of the streamed kernel for `n_images` images of `rows` x `width` x `channels` (row pitch 0 = tight)
+ * on a GPU that keeps `resident_ctas` CTAs of it resident (introspection for tests; needs no GPU).  `feed` != 0 plans the
+ * FEED form (n_images = images per batch at most).  out[] = {chunks per row, chunks per column block, column blocks,
+ * images per group, seg, nseg, seg_fine, nseg_fine, image blocks, coarse image blocks, first fine group, groups, margin,
+ * threads per CTA, dynamic shared memory bytes, rows end inside a chunk}.  Groups [0, first fine group) cut image blocks
+ * [0, coarse) into nseg segments of seg rows (x column blocks); the remaining groups cut the remaining image blocks
+ * into nseg_fine segments of seg_fine rows -- group order: image block, then segment, then column block. */
+B200BLUR_API int b200blur_plan_groups(int width, int rows, int channels, int64_t n_images, size_t row_pitch,
+                                      int resident_ctas, int feed, int64_t out[16]);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 B200BLUR_API int64_t b200blur_ctx_launch_count(const b200blur_ctx *ctx);
 
