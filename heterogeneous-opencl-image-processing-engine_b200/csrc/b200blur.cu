@@ -196,6 +196,18 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 size_t in_pitch_of(const b200blur_launch *l) { return l->in_row_pitch ? l->in_row_pitch : (size_t)l->width * l->channels; }
 size_t out_pitch_of(const b200blur_launch *l) { return l->out_row_pitch ? l->out_row_pitch : (size_t)l->width * l->channels; }
 
+// TIGHT input: rows of `in` (and the halo rows) may have any pitch >= width*channels and any alignment -- the streamed
+// kernel copies aligned supersets and re-aligns in shared memory -- as long as the OUTPUT side is 16-byte pitched/aligned.
+bool launch_tight_input(const b200blur_launch *l)
+{
+    if (l->channels < 1 || l->channels > 4) return false;
+    const size_t row_bytes = (size_t)l->width * l->channels;
+    if (row_bytes < 256 || in_pitch_of(l) > 4096) return false;          // whole-row mode only
+    if (out_pitch_of(l) % 16 != 0 || !aligned16(l->out)) return false;
+    if (l->n_images > 1 && l->out_image_stride % 16) return false;
+    return true;
+}
+
 bool launch_vectorised(const b200blur_launch *l)
 {
     if (l->channels < 1 || l->channels > 4) return false;
@@ -276,6 +288,7 @@ struct StreamCfg {
     StreamKernel fn[4];       // by channels-1: rows end on a chunk boundary
     StreamKernel fn_edge[4];  // by channels-1: rows end inside a chunk (pitched rows)
     StreamKernel fn_feed[4];  // by channels-1: FEED mode (per-batch descriptors; tight rows that end on a chunk boundary)
+    StreamKernel fn_tight[4]; // by channels-1: TIGHT input rows (row pitch = width*channels, any alignment), pitched output
 };
 
 template <int RB, int NS>
@@ -287,7 +300,9 @@ constexpr StreamCfg make_cfg()
                      {b200blur::blur_stream_kernel<1, RB, NS, true>, b200blur::blur_stream_kernel<2, RB, NS, true>,
                       b200blur::blur_stream_kernel<3, RB, NS, true>, b200blur::blur_stream_kernel<4, RB, NS, true>},
                      {b200blur::blur_stream_kernel<1, RB, NS, false, true>, b200blur::blur_stream_kernel<2, RB, NS, false, true>,
-                      b200blur::blur_stream_kernel<3, RB, NS, false, true>, b200blur::blur_stream_kernel<4, RB, NS, false, true>}};
+                      b200blur::blur_stream_kernel<3, RB, NS, false, true>, b200blur::blur_stream_kernel<4, RB, NS, false, true>},
+                     {b200blur::blur_stream_kernel<1, RB, NS, true, false, true>, b200blur::blur_stream_kernel<2, RB, NS, true, false, true>,
+                      b200blur::blur_stream_kernel<3, RB, NS, true, false, true>, b200blur::blur_stream_kernel<4, RB, NS, true, false, true>}};
 }
 
 // {rows per slot, slots}; index 0 is the default (B200BLUR_V2_CFG selects another for tuning runs)
@@ -301,10 +316,10 @@ bool stream_eligible(const b200blur::BandParams &p) { return p.row_bytes >= 256;
 // PRMT selectors that apply the right-edge clamp to the {wl, w, wr} window of the chunk holding the end of a row whose
 // length is not a multiple of 16 (see StreamParams): window byte idx takes the byte C positions earlier when it is one
 // of the C bytes just past the end of the row.  Selector nibbles index the 8 bytes of (previous word, this word).
-void edge_selectors(b200blur::StreamParams &sp, int row_bytes, int channels)
+void edge_selectors(b200blur::StreamParams &sp, int row_bytes, int channels, bool force_general = false)
 {
     const int v = row_bytes - (sp.cpr - 1) * 16;  // bytes of the row inside its last chunk, 1..16
-    sp.edge_general = (v != 16);
+    sp.edge_general = (v != 16) || force_general;   // (TIGHT kernels are compiled with the general right-edge code only)
     sp.edge_prev = 0;
     sp.sel_prev = 0x7654;
     for (int m = 0; m < 6; m++) sp.sel_last[m] = 0x7654;
@@ -342,13 +357,14 @@ struct StreamPlan {
 
 // Plans the streamed kernel for band geometry `p` (p.n_images images per launch, or -- feed -- per batch at most).
 // `slots_override` > 0: plan for that many resident CTAs without asking the CUDA runtime (host-side introspection).
-int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, StreamPlan &plan, long long slots_override = 0)
+int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, StreamPlan &plan, long long slots_override = 0,
+                bool tight = false)
 {
     b200blur::StreamParams &sp = plan.sp;
     memset(&sp, 0, sizeof sp);
     sp.b = p;
     sp.cpr = (p.row_bytes + 15) / 16;   // live chunks per row; bytes past row_bytes up to the pitch are padding
-    edge_selectors(sp, p.row_bytes, p.channels);
+    edge_selectors(sp, p.row_bytes, p.channels, tight);
     const StreamCfg &cfg = kStreamCfgs[(ctx->v2_cfg >= 0 && ctx->v2_cfg < kNumStreamCfgs) ? ctx->v2_cfg : 0];
     int threads;
     if (p.pitch <= 4096 && sp.cpr <= 256) {
@@ -371,7 +387,8 @@ int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, Str
         if (sp.ipc > p.n_images && p.n_images > 0) sp.ipc = (int)p.n_images;
         // Rows as they lie in memory (RB rows of an image = one bulk copy, padding included) while the padding is small;
         // heavily padded rows (ROI views, pitch >> width*channels) bring only their live chunks, one copy per row.
-        sp.margin = ((long long)p.pitch - sp.cpr * 16 > sp.cpr * 4) ? 16 : 0;
+        sp.margin = (!tight && (long long)p.pitch - sp.cpr * 16 > sp.cpr * 4) ? 16 : 0;
+        if (tight && sp.ipc > b200blur::kTightMaxLanes) sp.ipc = b200blur::kTightMaxLanes;
     } else {
         threads = ctx->v2_threads > 0 ? ctx->v2_threads : 128;
         if (threads > 256) threads = 256;
@@ -380,18 +397,22 @@ int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, Str
         sp.margin = 16;
         sp.ipc = 1;
     }
+    // TIGHT: an image lane of a slot = 16 B lead pad + up to three runs of rows, each widened to 16-byte boundaries
+    sp.lane_bytes = tight ? (cfg.rb * p.row_bytes + 15) / 16 * 16 + 128 : 0;
     auto smem_for = [&](int ipc) {
         const int sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;
-        return 16 + (size_t)cfg.ns * ipc * cfg.rb * sstride + 16 + 16 * cfg.ns + sizeof(b200blur::GroupMeta) * cfg.ns +
-               (feed ? 24 * b200blur::kFeedDepth : 0);
+        const size_t slot = tight ? (size_t)ipc * sp.lane_bytes : (size_t)ipc * cfg.rb * sstride;
+        return 16 + (size_t)cfg.ns * slot + 16 + 16 * cfg.ns + sizeof(b200blur::GroupMeta) * cfg.ns +
+               (feed ? 24 * b200blur::kFeedDepth : 0) + (tight ? 2 * cfg.ns * b200blur::kTightMaxLanes * cfg.rb : 0);
     };
     while (sp.ipc > 1 && smem_for(sp.ipc) > 200 * 1024) sp.ipc--;   // fewer images side by side rather than no launch
     sp.sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;   // whole rows land exactly as they lie in memory
-    sp.slot_bytes = sp.ipc * cfg.rb * sp.sstride;
+    sp.slot_bytes = tight ? sp.ipc * sp.lane_bytes : sp.ipc * cfg.rb * sp.sstride;
     plan.smem = smem_for(sp.ipc);
     plan.block = threads + (feed ? 64 : 32);  // + the producer warp (+ the accountant warp of a feed)
     if (plan.smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", plan.smem);
-    plan.fn = feed ? cfg.fn_feed[p.channels - 1] : sp.edge_general ? cfg.fn_edge[p.channels - 1] : cfg.fn[p.channels - 1];
+    plan.fn = tight ? cfg.fn_tight[p.channels - 1]
+              : feed ? cfg.fn_feed[p.channels - 1] : sp.edge_general ? cfg.fn_edge[p.channels - 1] : cfg.fn[p.channels - 1];
     int per_sm = slots_override > 0 ? 1 : 0;
     for (auto &ki : ctx->kernel_info)
         if (ki.fn == (const void *)plan.fn && ki.block == plan.block && ki.smem == plan.smem) per_sm = ki.per_sm;
@@ -486,10 +507,10 @@ int launch_planned(b200blur_ctx *ctx, const StreamPlan &plan, long long grid, cu
     return B200BLUR_OK;
 }
 
-int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s, int queue)
+int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s, int queue, bool tight = false)
 {
     StreamPlan plan;
-    if (int rc = plan_stream(ctx, p, false, plan)) return rc;
+    if (int rc = plan_stream(ctx, p, false, plan, 0, tight)) return rc;
     plan.sp.work = ctx->d_work + 2 * queue;
     const long long grid = plan.sp.n_groups < plan.slots ? plan.sp.n_groups : plan.slots;
     return launch_planned(ctx, plan, grid, s);
@@ -505,6 +526,9 @@ int do_launch(b200blur_ctx *ctx, int queue, const b200blur_launch *l, int *n_ker
     const bool vec = launch_vectorised(l);
     if (vec && stream_eligible(p) && ctx->kernel_variant != 1) {
         if (int rc = launch_stream(ctx, p, s, queue)) return rc;
+        ++*n_kernels;
+    } else if (!vec && launch_tight_input(l) && ctx->kernel_variant != 1) {
+        if (int rc = launch_stream(ctx, p, s, queue, true)) return rc;
         ++*n_kernels;
     } else if (vec && p.row_bytes % 16 == 0) {
         // strip height: tall strips amortise the two halo rows; short strips expose more threads for small batches
@@ -537,28 +561,37 @@ int do_launch(b200blur_ctx *ctx, int queue, const b200blur_launch *l, int *n_ker
 // tight <-> pitched row re-packing on stream s (see repitch_*_kernel); both pointers 16-byte aligned
 void launch_repitch_in(b200blur_ctx *ctx, cudaStream_t s, const void *tight, void *pitched, long long rows, int row_bytes, int pitch)
 {
-    const long long total = rows * ((row_bytes + 15) / 16);
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)ctx->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    b200blur::repitch_in_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const uint8_t *>(tight), static_cast<uint8_t *>(pitched),
-                                                                 rows, row_bytes, pitch);
-    ctx->launches++;
+    const long long per_block_rows = b200blur::kRepitchRows;
+    const long long total = per_block_rows * ((row_bytes + 15) / 16);
+    long long bx = (total + 255) / 256;
+    if (bx > 64) bx = 64;
+    const long long by = (rows + per_block_rows - 1) / per_block_rows;
+    for (long long y0 = 0; y0 < by; y0 += 65535) {   // grid.y limit
+        const long long ny = by - y0 < 65535 ? by - y0 : 65535;
+        const long long r0 = y0 * per_block_rows;
+        b200blur::repitch_in_kernel<<<dim3((unsigned)bx, (unsigned)ny), 256, 0, s>>>(
+            static_cast<const uint8_t *>(tight) + r0 * row_bytes, static_cast<uint8_t *>(pitched) + r0 * pitch, rows - r0, row_bytes, pitch);
+        ctx->launches++;
+    }
 }
 
 // `tight_base` is 16-byte aligned; the rows land at byte offset `lo` of it
 void launch_repitch_out(b200blur_ctx *ctx, cudaStream_t s, const void *pitched, void *tight_base, long long lo, long long rows,
                         int row_bytes, int pitch)
 {
-    const long long total = (rows * (long long)row_bytes + 15) / 16 + 1;
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)ctx->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    b200blur::repitch_out_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const uint8_t *>(pitched),
-                                                                  static_cast<uint8_t *>(tight_base), lo, rows, row_bytes, pitch);
-    ctx->launches++;
+    const long long per_block_rows = b200blur::kRepitchRows;
+    const long long total = (per_block_rows * row_bytes + 15) / 16 + 1;
+    long long bx = (total + 255) / 256;
+    if (bx > 64) bx = 64;
+    const long long by = (rows + per_block_rows - 1) / per_block_rows;
+    for (long long y0 = 0; y0 < by; y0 += 65535) {
+        const long long ny = by - y0 < 65535 ? by - y0 : 65535;
+        const long long r0 = y0 * per_block_rows;
+        b200blur::repitch_out_kernel<<<dim3((unsigned)bx, (unsigned)ny), 256, 0, s>>>(
+            static_cast<const uint8_t *>(pitched) + r0 * pitch, static_cast<uint8_t *>(tight_base), lo + r0 * row_bytes, rows - r0,
+            row_bytes, pitch);
+        ctx->launches++;
+    }
 }
 
 double now_ms()
@@ -1154,7 +1187,7 @@ int b200blur_plan_groups(int width, int rows, int channels, int64_t n_images, si
 int b200blur_launch_is_vectorised(const b200blur_launch *launch)
 {
     if (!launch) return 0;
-    return launch_vectorised(launch) ? 1 : 0;
+    return (launch_vectorised(launch) || launch_tight_input(launch)) ? 1 : 0;
 }
 
 int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200blur_launch *launch, b200blur_event *ev)
@@ -1363,23 +1396,26 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
     if (stats)
         if (int rc = event_begin(ctx, 0, &ev_all, &slot)) return rc;
     int64_t launches = 0;
-    // Odd widths (width*channels % 16 != 0): tight rows cannot be read 16 bytes at a time, so the stream is re-pitched
-    // through a scratch pair with strided device copies, ~128 MB at a time, and blurred on the vectorised path
-    // (3 passes over the data instead of the ~20x slower byte-wise generic kernel).
+    // Odd widths (width*channels % 16 != 0).  Rows up to 4 KB: the streamed kernel reads the tight rows as they are
+    // (TIGHT input: aligned-superset bulk copies, re-aligned in shared memory) and writes 16-byte-pitched rows into a
+    // scratch buffer, ~128 MB at a time, that one re-pack kernel turns back into tight rows: 2 passes over the data.
+    // Wider rows are re-pitched on the way in as well (3 passes; the byte-wise generic kernel would be ~20x slower).
     const size_t row_bytes = (size_t)width * channels;
+    static const bool env_no_tight = getenv("B200BLUR_NO_TIGHT") != nullptr;
     if (row_bytes % 16 != 0 && channels <= 4 && row_bytes >= 256 && n_images > 0 && height > 0) {
         const size_t dev_pitch = (row_bytes + 15) / 16 * 16;
         const size_t dev_image_bytes = dev_pitch * (size_t)height;
-        int64_t chunk = (int64_t)((128ull << 20) / dev_image_bytes);
+        int64_t chunk = (int64_t)((512ull << 20) / dev_image_bytes);   // scratch of up to 512 MB (x2 for wide rows)
         if (chunk < 1) chunk = 1;
         if (chunk > n_images) chunk = n_images;
         const size_t need = dev_image_bytes * (size_t)chunk;
-        if (ctx->scratch_bytes < need) {
+        const bool need_in = !(row_bytes <= 4096 && ctx->kernel_variant != 1 && !env_no_tight);   // TIGHT input needs no scratch_in
+        if (ctx->scratch_bytes < need || (need_in && !ctx->scratch_in)) {
             if (ctx->scratch_in) cudaFree(ctx->scratch_in);
             if (ctx->scratch_out) cudaFree(ctx->scratch_out);
             ctx->scratch_in = ctx->scratch_out = nullptr;
             ctx->scratch_bytes = 0;
-            CU_TRY(cudaMalloc((void **)&ctx->scratch_in, need));
+            if (need_in) CU_TRY(cudaMalloc((void **)&ctx->scratch_in, need));
             CU_TRY(cudaMalloc((void **)&ctx->scratch_out, need));
             ctx->scratch_bytes = need;
         }
@@ -1388,7 +1424,10 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
             const uint8_t *src = static_cast<const uint8_t *>(d_in) + (size_t)i0 * image_bytes;
             uint8_t *dst = static_cast<uint8_t *>(d_out) + (size_t)i0 * image_bytes;
             const bool fast_repack = aligned16(d_out);  // the re-pack kernel writes aligned 16-byte words of the tight output
-            if (fast_repack) {
+            const bool tight_in = row_bytes <= 4096 && ctx->kernel_variant != 1 && !env_no_tight;
+            if (tight_in) {
+                // nothing to do on the way in
+            } else if (fast_repack) {
                 launch_repitch_in(ctx, s, src, ctx->scratch_in, n * (long long)height, (int)row_bytes, (int)dev_pitch);
                 launches++;
             } else {
@@ -1396,8 +1435,10 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
                                          cudaMemcpyDeviceToDevice, s));
             }
             b200blur_launch l;
-            if (int rc = b200blur_launch_rows_pitched(&l, ctx->scratch_in, ctx->scratch_out, width, height, channels, 0,
-                                                      height, n, dev_image_bytes, dev_image_bytes, dev_pitch, dev_pitch))
+            if (int rc = tight_in ? b200blur_launch_rows_pitched(&l, src, ctx->scratch_out, width, height, channels, 0, height, n,
+                                                                 image_bytes, dev_image_bytes, 0, dev_pitch)
+                                  : b200blur_launch_rows_pitched(&l, ctx->scratch_in, ctx->scratch_out, width, height, channels, 0,
+                                                                 height, n, dev_image_bytes, dev_image_bytes, dev_pitch, dev_pitch))
                 return rc;
             int nk;
             if (int rc = do_launch(ctx, 0, &l, &nk)) return rc;
@@ -1638,6 +1679,8 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
     const bool repitch = row_bytes % 16 != 0 && channels <= 4 && row_bytes >= 256;
     const size_t dev_pitch = repitch ? (row_bytes + 15) / 16 * 16 : row_bytes;
     const size_t dev_image_bytes = dev_pitch * (size_t)height;
+    // rows up to 4 KB: the blur reads the tight upload as it is (TIGHT input), only the output is re-packed
+    const bool tight_in = repitch && row_bytes <= 4096 && ctx->kernel_variant != 1 && getenv("B200BLUR_NO_TIGHT") == nullptr;
     if (int rc = ring_prepare(ctx, dev_image_bytes * (size_t)batch_size, repitch ? image_bytes * (size_t)batch_size : 0, n_slots))
         return rc;
     cudaStream_t q_in = ctx->queues[0], q_k = ctx->queues[1], q_out = ctx->queues[2];
@@ -1672,11 +1715,13 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
             CU_TRY(cudaStreamWaitEvent(q_k, s.ev[1], 0));
             CU_TRY(cudaEventRecord(s.ev[2], q_k));
             b200blur_launch l;
-            if (int rc = b200blur_launch_rows_pitched(&l, s.d_in, s.d_out, width, height, channels, 0, height, n,
-                                                      dev_image_bytes, dev_image_bytes, repitch ? dev_pitch : 0,
-                                                      repitch ? dev_pitch : 0))
+            if (int rc = tight_in ? b200blur_launch_rows_pitched(&l, s.t_in, s.d_out, width, height, channels, 0, height, n, image_bytes,
+                                                                 dev_image_bytes, 0, dev_pitch)
+                                  : b200blur_launch_rows_pitched(&l, s.d_in, s.d_out, width, height, channels, 0, height, n,
+                                                                 dev_image_bytes, dev_image_bytes, repitch ? dev_pitch : 0,
+                                                                 repitch ? dev_pitch : 0))
                 return rc;
-            if (repitch && bytes) {
+            if (repitch && !tight_in && bytes) {
                 launch_repitch_in(ctx, q_k, s.t_in, s.d_in, n * (long long)height, (int)row_bytes, (int)dev_pitch);
                 launches++;
             }

@@ -236,7 +236,8 @@ struct StreamParams {
     int nseg;           // coarse segments per band
     int margin;         // 0 (whole rows, contiguous copies) or 16 (per-row copies: column blocks, heavily padded rows)
     int sstride;        // shared-memory row stride in bytes = cb*16 + 2*margin, or the row pitch when margin == 0
-    int slot_bytes;     // ipc * RB * sstride
+    int slot_bytes;     // ipc * RB * sstride (TIGHT: ipc * lane_bytes)
+    int lane_bytes;     // TIGHT: shared-memory bytes of one image lane of a slot (16 B lead pad + up to 3 runs of rows + slack)
     long long img_blocks;   // ceil(n_images / ipc)
     // Guided tail: image blocks [0, ib_coarse) are cut into `nseg` segments of `seg` rows, the remaining image blocks --
     // the last work handed out -- into `nseg_fine` segments of `seg_fine` rows, so that the CTAs run dry within a
@@ -410,6 +411,49 @@ __device__ __forceinline__ void decode_group(const StreamParams &sp, long long g
     out = sp.b.out + (size_t)img0 * sp.b.out_stride + (size_t)q.r0 * sp.b.out_pitch + q.x0;
 }
 
+// TIGHT rows (row pitch = width*channels, not a multiple of 16; any pointer alignment): consecutive rows of an image are
+// still one contiguous byte range, only not a 16-byte aligned one.  The producer copies the ALIGNED SUPERSET of each run
+// of rows (up to 15 bytes more at either end, inside the same 16-byte blocks as the run's first and last byte) and notes,
+// for every row of the slot, where its first byte landed (`rowoff`); the consumers read their 24-byte window at that
+// byte address with seven aligned 32-bit loads and six funnel shifts.  Nothing else changes: this folds the re-pitch
+// pass that used to run before the blur into the blur's own loads.
+template <int RB>
+__device__ __forceinline__ void stream_issue_slot_tight(const StreamParams &sp, const GroupGeom &q, int slot_in_item,
+                                                        uint32_t slot_smem, uint32_t bar, unsigned short *rowoff)
+{
+    const BandParams &b = sp.b;
+    const int k0 = slot_in_item * RB;
+    const int k1 = min(k0 + RB, q.nr + 2);
+    for (int il = 0; il < q.n_img; il++) {
+        const uint8_t *src = q.in + (size_t)il * b.in_stride;
+        const uint32_t lane_base = slot_smem + (uint32_t)(il * sp.lane_bytes) + 16u;
+        uint32_t cur = 0;   // aligned offset of the next run within the lane
+        int k = k0;
+        while (k < k1) {
+            const int j = q.r0 - 1 + k;
+            const uint8_t *rp;
+            int run = 1;
+            if (j < 0) {
+                rp = q.top ? q.top + (size_t)il * b.top_stride : src;
+            } else if (j >= b.rows) {
+                rp = q.bot ? q.bot + (size_t)il * b.bot_stride : src + (size_t)(b.rows - 1) * b.pitch;
+            } else {
+                rp = src + (size_t)j * b.pitch;
+                run = min(k1 - k, b.rows - j);
+            }
+            const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(rp) & 15u);
+            const uint32_t bytes = (delta + (uint32_t)run * (uint32_t)b.row_bytes + 15u) & ~15u;
+            for (int i = 0; i < run; i++)
+                rowoff[il * RB + (k - k0) + i] = (unsigned short)(cur + delta + (uint32_t)i * (uint32_t)b.pitch);
+            ptx::mbar_expect_tx(bar, bytes);
+            ptx::bulk_g2s(lane_base + cur, rp - delta, bytes, bar);
+            cur += bytes;
+            k += run;
+        }
+    }
+    ptx::mbar_arrive(bar);
+}
+
 template <int RB>
 __device__ __forceinline__ void stream_issue_slot(const StreamParams &sp, const GroupGeom &q, int slot_in_item,
                                                   uint32_t slot_smem, uint32_t bar)
@@ -479,7 +523,9 @@ constexpr int kFeedDepth = 8;   // group records in flight per CTA between produ
 // the consumers need to know about it next to the slot (meta[]), so SMs that see more bandwidth simply take more
 // groups.  (A static round-robin persistent grid loses ~10 % of HBM bandwidth on B200 -- tools/membench.cu.)
 // EDGE = rows that do not end on a chunk boundary (pitched rows); compiled separately so the aligned case pays nothing.
-template <int C, int RB, int NS, bool EDGE = false, bool FEED = false>
+constexpr int kTightMaxLanes = 16;   // image lanes per group in TIGHT mode (rows >= 256 bytes, <= 256 consumer threads)
+
+template <int C, int RB, int NS, bool EDGE = false, bool FEED = false, bool TIGHT = false>
 __global__ void __launch_bounds__((FEED ? 64 : 32) + 256)
 blur_stream_kernel(const StreamParams sp)
 {
@@ -493,6 +539,8 @@ blur_stream_kernel(const StreamParams sp)
     const uint32_t gdone = empty + 8 * NS + (uint32_t)sizeof(GroupMeta) * NS;
     const uint32_t gfree = gdone + 8 * kFeedDepth;
     int2 *grec = reinterpret_cast<int2 *>(reinterpret_cast<uint8_t *>(meta + NS) + 16 * kFeedDepth);
+    // TIGHT: [NS][kTightMaxLanes][RB] byte offsets of the rows of a slot within their image lane (after the group records)
+    unsigned short *rowoff = reinterpret_cast<unsigned short *>(meta + NS);
     const int t = threadIdx.x;
     constexpr int LEAD = FEED ? 64 : 32;   // threads before the consumers: producer warp (+ accountant warp)
     const int n_cwarps = ((int)blockDim.x - LEAD) >> 5;
@@ -652,6 +700,9 @@ blur_stream_kernel(const StreamParams sp)
                     ptx::mbar_wait(empty + 8 * buf, ((pcount / NS) & 1) ^ 1);
                     if (s == 0) meta[buf] = m;
                     if (done) ptx::mbar_arrive(full + 8 * buf);   // sentinel slot: no data, tells the consumers to stop
+                    else if (TIGHT)
+                        stream_issue_slot_tight<RB>(sp, q, s, ring + (uint32_t)(buf * sp.slot_bytes), full + 8 * buf,
+                                                    rowoff + buf * (kTightMaxLanes * RB));
                     else stream_issue_slot<RB>(sp, q, s, ring + (uint32_t)(buf * sp.slot_bytes), full + 8 * buf);
                 }
                 if (done) break;
@@ -684,7 +735,8 @@ blur_stream_kernel(const StreamParams sp)
         const bool prev_last = EDGE && ((m.flags >> 8) == c + 1);
         const int nslots = (m.nr + 2 + RB - 1) / RB;
         const int il_c = active ? il : 0, c_c = active ? c : 0;
-        const uint32_t lane_off = (uint32_t)(il_c * RB * sp.sstride + sp.margin + c_c * 16);
+        const uint32_t lane_off = TIGHT ? (uint32_t)(il_c * sp.lane_bytes + 16 + c_c * 16)
+                                        : (uint32_t)(il_c * RB * sp.sstride + sp.margin + c_c * 16);
         // Output row k-2 is produced when input row k of the item arrives: `dst` points two rows early.
         uint8_t *dst = m.out + (size_t)il_c * sp.b.out_stride + c_c * 16 - 2 * (ptrdiff_t)sp.b.out_pitch;
         // Rolling vertical state, pre-scaled by 16: before row k arrives
@@ -694,9 +746,25 @@ blur_stream_kernel(const StreamParams sp)
         for (int i = 0; i < 8; i++) accA[i] = accB[i] = 0;
         // one input row: horizontal sums, vertical roll, one 16-byte store (if `store`)
         auto row = [&](uint32_t a, uint8_t *out_row, bool store) {
-            uint4 w = ptx::lds128(a);
-            uint32_t wl = ptx::lds32(a - 4);
-            uint32_t wr = ptx::lds32(a + 16);
+            uint4 w;
+            uint32_t wl, wr;
+            if (!TIGHT) {
+                w = ptx::lds128(a);
+                wl = ptx::lds32(a - 4);
+                wr = ptx::lds32(a + 16);
+            } else {
+                // the 24-byte window {wl, w, wr} starts at the arbitrary byte address a - 4
+                const uint32_t a4 = (a - 4u) & ~3u, sh = ((a - 4u) & 3u) * 8u;
+                uint32_t x[7];
+#pragma unroll
+                for (int i = 0; i < 7; i++) x[i] = ptx::lds32(a4 + 4u * i);
+                wl = __funnelshift_r(x[0], x[1], sh);
+                w.x = __funnelshift_r(x[1], x[2], sh);
+                w.y = __funnelshift_r(x[2], x[3], sh);
+                w.z = __funnelshift_r(x[3], x[4], sh);
+                w.w = __funnelshift_r(x[4], x[5], sh);
+                wr = __funnelshift_r(x[5], x[6], sh);
+            }
             if (first) wl = w.x << (8 * (4 - C));   // clamp: pixel -1 := pixel 0        (gaussian_kernel.cl:56)
             if (!EDGE) {
                 if (last) wr = w.w >> (8 * (4 - C));    // clamp: pixel width := pixel width-1
@@ -730,24 +798,26 @@ blur_stream_kernel(const StreamParams sp)
             const int buf = ccount % NS;
             if (s > 0) ptx::mbar_wait(full + 8 * buf, (ccount / NS) & 1);
             const uint32_t a = ring + (uint32_t)(buf * sp.slot_bytes) + lane_off;
+            // TIGHT: where each row of this image lane starts (written by the producer before it released the slot)
+            const unsigned short *ro = rowoff + buf * (kTightMaxLanes * RB) + il_c * RB;
+            auto row_addr = [&](int r) -> uint32_t {
+                return TIGHT ? a + (uint32_t)ro[r] : a + (uint32_t)r * (uint32_t)sp.sstride;
+            };
             // Whole slots (the planner sizes groups so that nearly all are) run fully unrolled with compile-time row
             // offsets and no per-row trip test; the first slot of a group only differs in not storing rows 0 and 1.
             if (k_end - k >= RB) {
                 if (s == 0) {
 #pragma unroll
-                    for (int r = 0; r < RB; r++)
-                        row(a + (uint32_t)r * (uint32_t)sp.sstride, dst + (size_t)r * (size_t)sp.b.out_pitch, active && r >= 2);
+                    for (int r = 0; r < RB; r++) row(row_addr(r), dst + (size_t)r * (size_t)sp.b.out_pitch, active && r >= 2);
                 } else {
 #pragma unroll
-                    for (int r = 0; r < RB; r++)
-                        row(a + (uint32_t)r * (uint32_t)sp.sstride, dst + (size_t)r * (size_t)sp.b.out_pitch, active);
+                    for (int r = 0; r < RB; r++) row(row_addr(r), dst + (size_t)r * (size_t)sp.b.out_pitch, active);
                 }
                 k += RB;
             } else {
                 const int n = k_end - k;                // short last slot of a group (uniform across the CTA)
 #pragma unroll 1
-                for (int r = 0; r < n; r++)
-                    row(a + (uint32_t)r * (uint32_t)sp.sstride, dst + (size_t)r * (size_t)sp.b.out_pitch, active && k + r >= 2);
+                for (int r = 0; r < n; r++) row(row_addr(r), dst + (size_t)r * (size_t)sp.b.out_pitch, active && k + r >= 2);
                 k += n;
             }
             dst += (size_t)RB * (size_t)sp.b.out_pitch;
@@ -786,45 +856,75 @@ __device__ __forceinline__ uint4 load_unaligned16(const uint8_t *p, const uint8_
     return r;
 }
 
-// tight [rows][row_bytes] -> pitched [rows][pitch]; grid.x covers chunks of a row, grid.y/z-free: rows flattened in x.
+// tight [rows][row_bytes] -> pitched [rows][pitch].  blockIdx.y = block of kRepitchRows rows (all index arithmetic inside
+// a block of rows is 32-bit: a 64-bit division per 16 bytes made these kernels ALU-bound), blockIdx.x/threads = 16-byte
+// chunks of those rows.
+constexpr int kRepitchRows = 128;
 __global__ void __launch_bounds__(256)
 repitch_in_kernel(const uint8_t *__restrict__ tight, uint8_t *__restrict__ pitched, long long rows, int row_bytes, int pitch)
 {
-    const int cpr = (row_bytes + 15) / 16;
-    const long long total = rows * cpr;
+    const long long row0 = (long long)blockIdx.y * kRepitchRows;
+    const int nrows = (int)min((long long)kRepitchRows, rows - row0);
+    const unsigned cpr = (unsigned)(row_bytes + 15) / 16;
+    const unsigned total = (unsigned)nrows * cpr;
     const uint8_t *end = tight + rows * (long long)row_bytes;
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-        const long long r = g / cpr;
-        const int c = (int)(g - r * cpr);
-        const uint4 v = load_unaligned16(tight + r * (long long)row_bytes + 16 * c, end);
-        *reinterpret_cast<uint4 *>(pitched + r * (long long)pitch + 16 * c) = v;
+    const uint8_t *src = tight + row0 * (long long)row_bytes;
+    uint8_t *dst = pitched + row0 * (long long)pitch;
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+        const unsigned r = g / cpr, c = g - r * cpr;
+        const uint4 v = load_unaligned16(src + (size_t)r * row_bytes + 16 * c, end);
+        *reinterpret_cast<uint4 *>(dst + (size_t)r * pitch + 16 * c) = v;
     }
 }
 
 // pitched [rows][pitch] -> rows [lo/row_bytes, ...) of a tight buffer; one thread per aligned 16-byte word of the tight
 // buffer.  `tight` is the 16-byte aligned base, [lo, lo + rows*row_bytes) the byte range that belongs to these rows: words
-// only partly inside the range (its two ends) and words that straddle two rows are written byte by byte.
+// only partly inside a row block's range (its two ends: the neighbouring block writes the other bytes) and words that
+// straddle two rows are written byte by byte.
 __global__ void __launch_bounds__(256)
 repitch_out_kernel(const uint8_t *__restrict__ pitched, uint8_t *__restrict__ tight, long long lo, long long rows, int row_bytes,
                    int pitch)
 {
-    const long long hi = lo + rows * (long long)row_bytes;
-    const long long w0 = lo / 16, w1 = (hi + 15) / 16;
+    const long long row0 = (long long)blockIdx.y * kRepitchRows;
+    const unsigned nrows = (unsigned)min((long long)kRepitchRows, rows - row0);
+    const long long blo = lo + row0 * (long long)row_bytes;          // this row block's byte range of the tight buffer
+    const unsigned span = nrows * (unsigned)row_bytes;
+    const long long w0 = blo / 16;                                    // first aligned word that holds a byte of the range
+    const unsigned head = (unsigned)(blo - w0 * 16);                  // bytes of that word before the range
+    const unsigned n_words = (head + span + 15) / 16;
+    const uint8_t *src = pitched + row0 * (long long)pitch;
     const uint8_t *end = pitched + rows * (long long)pitch;
-    for (long long g = w0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < w1; g += (long long)gridDim.x * blockDim.x) {
-        const long long b0 = g * 16;
-        const long long r = (b0 - lo) / row_bytes;          // row within this range (valid when b0 >= lo)
-        const long long col = (b0 - lo) - r * row_bytes;
-        if (b0 >= lo && b0 + 16 <= hi && col + 16 <= row_bytes) {   // the whole word comes from one row
-            const uint4 v = load_unaligned16(pitched + r * (long long)pitch + col, end);
-            *reinterpret_cast<uint4 *>(tight + b0) = v;
-        } else {
-            for (int i = 0; i < 16; i++) {
-                const long long b = b0 + i;
-                if (b < lo || b >= hi) continue;
-                const long long rr = (b - lo) / row_bytes;
-                tight[b] = pitched[rr * (long long)pitch + ((b - lo) - rr * row_bytes)];
+    uint8_t *dst = tight + w0 * 16;
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_words; g += gridDim.x * blockDim.x) {
+        const int b0 = (int)(g * 16) - (int)head;                     // offset of the word's first byte within the range
+        if (b0 >= 0 && (unsigned)b0 + 16 <= span) {
+            const unsigned r = (unsigned)b0 / (unsigned)row_bytes, col = (unsigned)b0 - r * (unsigned)row_bytes;
+            if (col + 16 <= (unsigned)row_bytes) {                    // the whole word comes from one row
+                *reinterpret_cast<uint4 *>(dst + (size_t)g * 16) = load_unaligned16(src + (size_t)r * pitch + col, end);
+                continue;
             }
+            // The word straddles rows r and r+1 (one word per row does: a byte loop here would stall every warp).
+            // First k bytes = the end of row r, the other 16-k = the start of row r+1, read k bytes early so that they
+            // sit at the same byte positions; merge with byte masks.
+            const unsigned k = (unsigned)row_bytes - col;             // 1..15
+            const uint4 a = load_unaligned16(src + (size_t)r * pitch + col, end);
+            const uint4 bq = load_unaligned16(src + (size_t)(r + 1) * pitch - k, end);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int nb = (int)k - 4 * i;                        // bytes of word i that come from row r
+                const uint32_t m = nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
+                o[i] = (aw[i] & m) | (bw[i] & ~m);
+            }
+            *reinterpret_cast<uint4 *>(dst + (size_t)g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            continue;
+        }
+        for (int i = 0; i < 16; i++) {
+            const int b = b0 + i;
+            if (b < 0 || (unsigned)b >= span) continue;
+            const unsigned rr = (unsigned)b / (unsigned)row_bytes;
+            dst[(size_t)g * 16 + i] = src[(size_t)rr * pitch + ((unsigned)b - rr * (unsigned)row_bytes)];
         }
     }
 }

@@ -135,9 +135,11 @@ B200BLUR_API int b200blur_finish_all(b200blur_ctx *ctx);
  * for out / halo_top / halo_bottom with their own strides.  Halo pointers may address another GPU's memory
  * (peer-enabled or IPC-opened): the kernel then loads those rows over NVLink itself -- that is Approach 2's
  * halo exchange fused into the stencil.
- * in == out (in place) is not allowed.  The vectorised path needs channels <= 4, 16-byte aligned pointers/strides
- * and a row pitch that is a multiple of 16 (tight rows with width*channels % 16 == 0, or in/out_row_pitch set);
- * anything else runs the generic path (same results).
+ * in == out (in place) is not allowed.  The vectorised path needs channels <= 4 and, on the OUTPUT side, 16-byte aligned
+ * pointers/strides and a row pitch that is a multiple of 16 (tight rows with width*channels % 16 == 0, or out_row_pitch
+ * set).  The INPUT side (in, halo rows) may then be tight rows of any length and alignment up to 4096 bytes per row --
+ * the kernel copies aligned supersets and re-aligns them in shared memory -- or 16-byte pitched/aligned rows of any
+ * length.  Anything else runs the generic path (same results).
  */
 typedef struct b200blur_launch {
     const void *in;

@@ -329,6 +329,60 @@ def test_failed_launch_releases_its_event(ctx):
     ctx.dev_free(d)
 
 
+def _blur_tight_in(ctx, x, first_row=0, n_rows=None, offset=0, halo_split=False):
+    """Tight (unaligned) input rows at device address base+offset, 16-byte-pitched output; optional row range / halo rows
+    taken from SEPARATE tight allocations (so their addresses have their own alignment)."""
+    n, h, w, c = x.shape
+    P = w * c
+    n_rows = h - first_row if n_rows is None else n_rows
+    pitch = (P + 15) // 16 * 16
+    d_in = ctx.dev_alloc(x.nbytes + 64)
+    d_out = ctx.dev_alloc(n * n_rows * pitch + 64)
+    ctx.enqueue_write(0, d_in + offset, x, x.nbytes)
+    l = ctx.launch_rows(d_in + offset, d_out, w, h, c, first_row, n_rows, n, in_row_pitch=0, out_row_pitch=pitch,
+                        in_image_stride=h * P, out_image_stride=n_rows * pitch)
+    extra = []
+    if halo_split:   # halo rows in their own buffers, at odd offsets
+        for name, row, off in (("halo_top", first_row - 1, 5), ("halo_bottom", first_row + n_rows, 11)):
+            if 0 <= row < h:
+                rows = np.ascontiguousarray(x[:, row])
+                d = ctx.dev_alloc(rows.nbytes + 64)
+                ctx.enqueue_write(0, d + off, rows, rows.nbytes)
+                setattr(l, name, d + off)
+                setattr(l, name + "_stride", P)
+                extra.append(d)
+    assert ctx.is_vectorised(l)
+    ctx.enqueue_blur(0, l)
+    out = np.zeros((n, n_rows, w, c), np.uint8)
+    ctx.enqueue_read_2d(0, out, P, d_out, pitch, P, n * n_rows)
+    ctx.finish()
+    for d in [d_in, d_out] + extra:
+        ctx.dev_free(d)
+    return out
+
+
+@pytest.mark.parametrize("shape", [(3, 37, 250, 3), (5, 20, 100, 3), (4, 9, 86, 3), (2, 64, 341, 3), (7, 33, 257, 1), (2, 17, 130, 2),
+                                   (3, 12, 67, 4), (2, 8, 1365, 3), (1, 5, 1000, 3), (9, 3, 90, 3)])
+def test_tight_input_rows_run_on_the_streamed_kernel(ctx, shape):
+    """Rows that are neither 16-byte pitched nor 16-byte aligned are read as they are (aligned-superset bulk copies,
+    re-aligned in shared memory): whole images, at a misaligned base address, a row range with implicit halo rows, and a
+    row range whose halo rows live in separate misaligned buffers (Approach 2 bands of an odd-width image)."""
+    n, h, w, c = shape
+    x = synth(sum(shape) * 7, n, h, w, c)
+    want = oracle.c_blur_batch(x)
+    assert_same(_blur_tight_in(ctx, x), want)
+    assert_same(_blur_tight_in(ctx, x, offset=3), want)
+    if h >= 4:
+        assert_same(_blur_tight_in(ctx, x, first_row=1, n_rows=h - 2), want[:, 1:h - 1])
+        assert_same(_blur_tight_in(ctx, x, first_row=1, n_rows=h - 2, offset=7, halo_split=True), want[:, 1:h - 1])
+
+
+def test_misaligned_input_with_aligned_row_length(ctx):
+    """width*channels a multiple of 16 but the input pointer is not 16-byte aligned (a view into a larger buffer)."""
+    x = synth(99, 4, 30, 320, 3)
+    assert_same(_blur_tight_in(ctx, x, offset=9), oracle.c_blur_batch(x))
+
+
 @pytest.mark.parametrize("n,h,w,c", [(300, 37, 250, 3), (40, 100, 341, 3), (3, 700, 1366, 3)])
 def test_run_resident_repitches_odd_widths(ctx, n, h, w, c):
     import torch
