@@ -50,9 +50,10 @@ for p in (ROOT, PKG):
 N_IMAGES, HEIGHT, WIDTH, CHANNELS, BATCH = 5000, 240, 320, 3, 35
 IMAGE_BYTES = HEIGHT * WIDTH * CHANNELS
 ALGO_BYTES_PER_IMAGE = 2 * IMAGE_BYTES  # every input byte read once, every output byte written once
-METRIC = "images/sec (3x3 Gaussian blur stream; value = device-resident, e2e = incl. host<->device copies)"
+METRIC = ("images/sec (3x3 Gaussian blur stream; value = device-resident with the batches of 35 fused into one launch, "
+          "per_batch = one work descriptor per batch, e2e = incl. host<->device copies)")
 UNIT = "images/s"
-WORKLOAD = "A1 image-level: 5000x 320x240 RGB uint8 per GPU, batch_size=35 (BASELINE.json configs[1])"
+WORKLOAD = "A1 image-level: 5000x 320x240 RGB uint8 per GPU, batch_size=35 (BASELINE.json configs[1]); batches fused for `value`"
 DTYPE = "u8 (exact integer arithmetic in packed 16-bit lanes)"
 
 

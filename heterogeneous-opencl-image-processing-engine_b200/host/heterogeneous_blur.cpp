@@ -156,7 +156,12 @@ int main(int argc, char **argv)
     // keep >= 16 pipeline steps per GPU (and, when the GPUs take work dynamically, enough steps to balance them)
     fuse = std::max(1LL, std::min<long long>(fuse, std::max(1, NUM_BATCHES / (stealing ? 16 * G : 16))));
     if (opt.fuse > 0) fuse = opt.fuse;
-    const long long slot_images = max_share * fuse;
+    // ring slot = `fuse` batch shares, or -- for batches far above the ~64 MB transfer size -- an even piece of one share
+    long long slot_images = max_share * fuse;
+    if (fuse == 1 && (double)max_share * image_size > 96.0 * 1024 * 1024 && opt.fuse <= 0) {
+        const long long pieces = (long long)((double)max_share * image_size / (64.0 * 1024 * 1024) + 0.5);
+        slot_images = (max_share + pieces - 1) / pieces;
+    }
     for (int k = 0; k < G; k++) {
         Worker &w = workers[k];
         w.gpu = k;
@@ -290,26 +295,31 @@ int main(int argc, char **argv)
                 count += c;
             }
             if (count == 0) continue;
-            Slot &s = w.ring[issued % kRing];
-            if (s.busy) harvest(w, s);
-            s.count = count;
-            s.first_image = first_image;
-            // CREATE BATCH IMAGE STREAM (:431-442): replicate the source image into this share's staging slots
-            const double tf = get_time_ms();
-            w.staging->replicate(s.h_in, original_image, image_size, count);
-            w.t.fill_ms += get_time_ms() - tf;
-            const size_t bytes = (size_t)count * image_size;
-            blur_check(b200blur_enqueue_write(w.ctx, 0, s.d_in, s.h_in, bytes, &s.ev_in), "GPU write failed");
-            blur_check(b200blur_enqueue_wait(w.ctx, 1, s.ev_in), "GPU wait failed");
-            b200blur_launch l;
-            blur_check(b200blur_launch_rows(&l, s.d_in, s.d_out, width, height, channels, 0, height, count, image_size, image_size),
-                       "Failed to set kernel args");
-            blur_check(b200blur_enqueue_blur(w.ctx, 1, &l, &s.ev_k), "GPU kernel launch failed");
-            blur_check(b200blur_enqueue_wait(w.ctx, 2, s.ev_k), "GPU wait failed");
-            blur_check(b200blur_enqueue_read(w.ctx, 2, s.h_out, s.d_out, bytes, &s.ev_out), "GPU read failed");
-            s.busy = true;
-            w.t.images += count;
-            issued++;
+            // a share larger than a ring slot (a big batch_size) moves in slot-sized pieces: images are independent
+            for (long long done = 0; done < count;) {
+                const long long piece = std::min(slot_images, count - done);
+                Slot &s = w.ring[issued % kRing];
+                if (s.busy) harvest(w, s);
+                s.count = piece;
+                s.first_image = first_image + done;
+                // CREATE BATCH IMAGE STREAM (:431-442): replicate the source image into this share's staging slots
+                const double tf = get_time_ms();
+                w.staging->replicate(s.h_in, original_image, image_size, piece);
+                w.t.fill_ms += get_time_ms() - tf;
+                const size_t bytes = (size_t)piece * image_size;
+                blur_check(b200blur_enqueue_write(w.ctx, 0, s.d_in, s.h_in, bytes, &s.ev_in), "GPU write failed");
+                blur_check(b200blur_enqueue_wait(w.ctx, 1, s.ev_in), "GPU wait failed");
+                b200blur_launch l;
+                blur_check(b200blur_launch_rows(&l, s.d_in, s.d_out, width, height, channels, 0, height, piece, image_size, image_size),
+                           "Failed to set kernel args");
+                blur_check(b200blur_enqueue_blur(w.ctx, 1, &l, &s.ev_k), "GPU kernel launch failed");
+                blur_check(b200blur_enqueue_wait(w.ctx, 2, s.ev_k), "GPU wait failed");
+                blur_check(b200blur_enqueue_read(w.ctx, 2, s.h_out, s.d_out, bytes, &s.ev_out), "GPU read failed");
+                s.busy = true;
+                w.t.images += piece;
+                issued++;
+                done += piece;
+            }
         }
         for (auto &s : w.ring)
             if (s.busy) harvest(w, s);

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """tools/sweep.py -- BASELINE.json configs[3]: batch-size sweep {1,35,50,100,200,500,800,1200} on 50k x 256x256 RGB,
-device-resident (coalesced and one-launch-per-batch) vs end-to-end (pinned host buffers, H2D+D2H in the timed region).
+device-resident -- batches fused (coalesce=1), one work descriptor per batch through the feed kernel (coalesce=0), one
+kernel launch per batch (coalesce=2) -- vs end-to-end (pinned host buffers, H2D+D2H in the timed region).
 Prints CSV: batch_size, mode, ms, img_per_sec, algorithmic_GBps (resident) or host_link_GBps_each_way (e2e), launches."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,8 +23,8 @@ def main():
     img_bytes = h * w * c
     print("batch_size,mode,ms,img_per_sec,GBps,launches")
     for b in (1, 35, 50, 100, 200, 500, 800, 1200):
-        for mode in ("resident_coalesced", "resident_per_batch", "end_to_end"):
-            if mode == "resident_per_batch" and b == 1 and n > 5000:
+        for mode in ("resident_coalesced", "resident_per_batch_descriptor", "resident_per_batch_launch", "end_to_end"):
+            if mode == "resident_per_batch_launch" and b == 1 and n > 5000:
                 nn = 5000  # 50k single-image launches would only measure the host launch rate for longer
             else:
                 nn = n if mode != "end_to_end" else n_e2e
@@ -36,7 +37,9 @@ def main():
                     e1 = ctx.enqueue_marker(2)
                 else:
                     e0 = ctx.enqueue_marker(0)
-                    ctx.run_resident(d_in, d_out, w, h, c, nn, b, mode == "resident_coalesced", stats=False)
+                    ctx.run_resident(d_in, d_out, w, h, c, nn, b,
+                                     {"resident_coalesced": 1, "resident_per_batch_descriptor": 0, "resident_per_batch_launch": 2}[mode],
+                                     stats=False)
                     e1 = ctx.enqueue_marker(0)
                 ctx.finish()
                 ms = ctx.elapsed_ms(e0, e1)
