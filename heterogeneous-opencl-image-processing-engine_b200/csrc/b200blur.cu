@@ -208,6 +208,15 @@ bool launch_tight_input(const b200blur_launch *l)
     return true;
 }
 
+// TIGHT input AND output: tight rows (pitch = width*channels) of any alignment on both sides, rows of 256..4096 bytes.
+bool launch_tight_inout(const b200blur_launch *l)
+{
+    if (l->channels < 1 || l->channels > 4) return false;
+    const size_t row_bytes = (size_t)l->width * l->channels;
+    if (row_bytes < 256 || in_pitch_of(l) > 4096) return false;
+    return out_pitch_of(l) == row_bytes;
+}
+
 bool launch_vectorised(const b200blur_launch *l)
 {
     if (l->channels < 1 || l->channels > 4) return false;
@@ -289,6 +298,7 @@ struct StreamCfg {
     StreamKernel fn_edge[4];  // by channels-1: rows end inside a chunk (pitched rows)
     StreamKernel fn_feed[4];  // by channels-1: FEED mode (per-batch descriptors; tight rows that end on a chunk boundary)
     StreamKernel fn_tight[4]; // by channels-1: TIGHT input rows (row pitch = width*channels, any alignment), pitched output
+    StreamKernel fn_tight2[4];  // by channels-1: TIGHT input and output rows (store warps)
 };
 
 template <int RB, int NS>
@@ -301,8 +311,10 @@ constexpr StreamCfg make_cfg()
                       b200blur::blur_stream_kernel<3, RB, NS, true>, b200blur::blur_stream_kernel<4, RB, NS, true>},
                      {b200blur::blur_stream_kernel<1, RB, NS, false, true>, b200blur::blur_stream_kernel<2, RB, NS, false, true>,
                       b200blur::blur_stream_kernel<3, RB, NS, false, true>, b200blur::blur_stream_kernel<4, RB, NS, false, true>},
-                     {b200blur::blur_stream_kernel<1, RB, NS, true, false, true>, b200blur::blur_stream_kernel<2, RB, NS, true, false, true>,
-                      b200blur::blur_stream_kernel<3, RB, NS, true, false, true>, b200blur::blur_stream_kernel<4, RB, NS, true, false, true>}};
+                     {b200blur::blur_stream_kernel<1, RB, NS, true, false, 1>, b200blur::blur_stream_kernel<2, RB, NS, true, false, 1>,
+                      b200blur::blur_stream_kernel<3, RB, NS, true, false, 1>, b200blur::blur_stream_kernel<4, RB, NS, true, false, 1>},
+                     {b200blur::blur_stream_kernel<1, RB, NS, true, false, 2>, b200blur::blur_stream_kernel<2, RB, NS, true, false, 2>,
+                      b200blur::blur_stream_kernel<3, RB, NS, true, false, 2>, b200blur::blur_stream_kernel<4, RB, NS, true, false, 2>}};
 }
 
 // {rows per slot, slots}; index 0 is the default (B200BLUR_V2_CFG selects another for tuning runs)
@@ -358,14 +370,15 @@ struct StreamPlan {
 // Plans the streamed kernel for band geometry `p` (p.n_images images per launch, or -- feed -- per batch at most).
 // `slots_override` > 0: plan for that many resident CTAs without asking the CUDA runtime (host-side introspection).
 int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, StreamPlan &plan, long long slots_override = 0,
-                bool tight = false)
+                int tight = 0)   // tight: 0 pitched rows, 1 tight input, 2 tight input and output
 {
     b200blur::StreamParams &sp = plan.sp;
     memset(&sp, 0, sizeof sp);
     sp.b = p;
     sp.cpr = (p.row_bytes + 15) / 16;   // live chunks per row; bytes past row_bytes up to the pitch are padding
-    edge_selectors(sp, p.row_bytes, p.channels, tight);
-    const StreamCfg &cfg = kStreamCfgs[(ctx->v2_cfg >= 0 && ctx->v2_cfg < kNumStreamCfgs) ? ctx->v2_cfg : 0];
+    edge_selectors(sp, p.row_bytes, p.channels, tight != 0);
+    // (tight output stages a second copy of every slot in shared memory: a 3-slot ring keeps 3 CTAs per SM)
+    const StreamCfg &cfg = kStreamCfgs[tight == 2 ? 1 : (ctx->v2_cfg >= 0 && ctx->v2_cfg < kNumStreamCfgs) ? ctx->v2_cfg : 0];
     int threads;
     if (p.pitch <= 4096 && sp.cpr <= 256) {
         // whole rows: a CTA step covers `ipc` images side by side; pick the block size that wastes fewest lanes
@@ -399,19 +412,24 @@ int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, Str
     }
     // TIGHT: an image lane of a slot = 16 B lead pad + up to three runs of rows, each widened to 16-byte boundaries
     sp.lane_bytes = tight ? (cfg.rb * p.row_bytes + 15) / 16 * 16 + 128 : 0;
+    sp.stage_pitch = tight == 2 ? (p.row_bytes + 15) / 16 * 16 : 0;
     auto smem_for = [&](int ipc) {
         const int sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;
         const size_t slot = tight ? (size_t)ipc * sp.lane_bytes : (size_t)ipc * cfg.rb * sstride;
         return 16 + (size_t)cfg.ns * slot + 16 + 16 * cfg.ns + sizeof(b200blur::GroupMeta) * cfg.ns +
-               (feed ? 24 * b200blur::kFeedDepth : 0) + (tight ? 2 * cfg.ns * b200blur::kTightMaxLanes * cfg.rb : 0);
+               (feed ? 24 * b200blur::kFeedDepth : 0) + (tight ? 2 * cfg.ns * b200blur::kTightMaxLanes * cfg.rb : 0) +
+               (tight == 2 ? 16 * b200blur::kStageSlots + sizeof(b200blur::StageRec) * b200blur::kStageRecs + 16 +
+                                 (size_t)b200blur::kStageSlots * ipc * cfg.rb * sp.stage_pitch + 16
+                           : 0);
     };
     while (sp.ipc > 1 && smem_for(sp.ipc) > 200 * 1024) sp.ipc--;   // fewer images side by side rather than no launch
     sp.sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;   // whole rows land exactly as they lie in memory
     sp.slot_bytes = tight ? sp.ipc * sp.lane_bytes : sp.ipc * cfg.rb * sp.sstride;
+    sp.stage_slot_bytes = sp.ipc * cfg.rb * sp.stage_pitch;
     plan.smem = smem_for(sp.ipc);
-    plan.block = threads + (feed ? 64 : 32);  // + the producer warp (+ the accountant warp of a feed)
+    plan.block = threads + (feed ? 64 : tight == 2 ? 32 + 32 * b200blur::kStoreWarps : 32);  // + producer (+ accountant / store warps)
     if (plan.smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", plan.smem);
-    plan.fn = tight ? cfg.fn_tight[p.channels - 1]
+    plan.fn = tight == 2 ? cfg.fn_tight2[p.channels - 1] : tight ? cfg.fn_tight[p.channels - 1]
               : feed ? cfg.fn_feed[p.channels - 1] : sp.edge_general ? cfg.fn_edge[p.channels - 1] : cfg.fn[p.channels - 1];
     int per_sm = slots_override > 0 ? 1 : 0;
     for (auto &ki : ctx->kernel_info)
@@ -507,7 +525,7 @@ int launch_planned(b200blur_ctx *ctx, const StreamPlan &plan, long long grid, cu
     return B200BLUR_OK;
 }
 
-int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s, int queue, bool tight = false)
+int launch_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, cudaStream_t s, int queue, int tight = 0)
 {
     StreamPlan plan;
     if (int rc = plan_stream(ctx, p, false, plan, 0, tight)) return rc;
@@ -528,7 +546,10 @@ int do_launch(b200blur_ctx *ctx, int queue, const b200blur_launch *l, int *n_ker
         if (int rc = launch_stream(ctx, p, s, queue)) return rc;
         ++*n_kernels;
     } else if (!vec && launch_tight_input(l) && ctx->kernel_variant != 1) {
-        if (int rc = launch_stream(ctx, p, s, queue, true)) return rc;
+        if (int rc = launch_stream(ctx, p, s, queue, 1)) return rc;
+        ++*n_kernels;
+    } else if (!vec && launch_tight_inout(l) && ctx->kernel_variant != 1 && !getenv("B200BLUR_NO_TIGHT_OUT")) {
+        if (int rc = launch_stream(ctx, p, s, queue, 2)) return rc;
         ++*n_kernels;
     } else if (vec && p.row_bytes % 16 == 0) {
         // strip height: tall strips amortise the two halo rows; short strips expose more threads for small batches
@@ -1176,7 +1197,7 @@ int b200blur_plan_groups(int width, int rows, int channels, int64_t n_images, si
     p.channels = channels;
     p.n_images = n_images;
     StreamPlan plan;
-    if (int rc = plan_stream(&tmp, p, feed != 0, plan, resident_ctas)) return rc;
+    if (int rc = plan_stream(&tmp, p, feed != 0, plan, resident_ctas, 0)) return rc;
     const b200blur::StreamParams &sp = plan.sp;
     const int64_t v[16] = {sp.cpr, sp.cb, sp.ncb, sp.ipc, sp.seg, sp.nseg, sp.seg_fine, sp.nseg_fine, sp.img_blocks, sp.ib_coarse,
                            sp.g_coarse, sp.n_groups, sp.margin, plan.block, (int64_t)plan.smem, sp.edge_general};
@@ -1187,7 +1208,7 @@ int b200blur_plan_groups(int width, int rows, int channels, int64_t n_images, si
 int b200blur_launch_is_vectorised(const b200blur_launch *launch)
 {
     if (!launch) return 0;
-    return (launch_vectorised(launch) || launch_tight_input(launch)) ? 1 : 0;
+    return (launch_vectorised(launch) || launch_tight_input(launch) || launch_tight_inout(launch)) ? 1 : 0;
 }
 
 int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200blur_launch *launch, b200blur_event *ev)
@@ -1396,13 +1417,16 @@ int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void *d_out, int 
     if (stats)
         if (int rc = event_begin(ctx, 0, &ev_all, &slot)) return rc;
     int64_t launches = 0;
-    // Odd widths (width*channels % 16 != 0).  Rows up to 4 KB: the streamed kernel reads the tight rows as they are
-    // (TIGHT input: aligned-superset bulk copies, re-aligned in shared memory) and writes 16-byte-pitched rows into a
-    // scratch buffer, ~128 MB at a time, that one re-pack kernel turns back into tight rows: 2 passes over the data.
-    // Wider rows are re-pitched on the way in as well (3 passes; the byte-wise generic kernel would be ~20x slower).
+    // Odd widths (width*channels % 16 != 0).  Rows up to 4 KB need nothing special: the streamed kernel reads the tight
+    // rows as they are (aligned-superset bulk copies, re-aligned in shared memory) and its store warps write tight rows
+    // (one pass).  With B200BLUR_NO_TIGHT_OUT only the input side is folded: 16-byte-pitched rows go to a scratch buffer
+    // that one re-pack kernel turns back into tight rows (2 passes).  Rows wider than 4 KB are re-pitched on the way in
+    // as well (3 passes; the byte-wise generic kernel would be ~20x slower).
     const size_t row_bytes = (size_t)width * channels;
     static const bool env_no_tight = getenv("B200BLUR_NO_TIGHT") != nullptr;
-    if (row_bytes % 16 != 0 && channels <= 4 && row_bytes >= 256 && n_images > 0 && height > 0) {
+    // rows up to 4 KB run in ONE pass: the streamed kernel reads and writes the tight rows itself (TIGHT input and output)
+    const bool one_pass = row_bytes <= 4096 && ctx->kernel_variant != 1 && !env_no_tight && !getenv("B200BLUR_NO_TIGHT_OUT");
+    if (row_bytes % 16 != 0 && channels <= 4 && row_bytes >= 256 && n_images > 0 && height > 0 && !one_pass) {
         const size_t dev_pitch = (row_bytes + 15) / 16 * 16;
         const size_t dev_image_bytes = dev_pitch * (size_t)height;
         int64_t chunk = (int64_t)((512ull << 20) / dev_image_bytes);   // scratch of up to 512 MB (x2 for wide rows)
@@ -1676,7 +1700,8 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
     // copy engines' strided copies manage only 6.5 GB/s on 750-byte rows) and are re-pitched to a multiple of 16 bytes
     // on the device by two small kernels around the blur, so the vectorised kernel runs on any image width.
     const size_t row_bytes = (size_t)width * channels;
-    const bool repitch = row_bytes % 16 != 0 && channels <= 4 && row_bytes >= 256;
+    const bool one_pass = row_bytes <= 4096 && ctx->kernel_variant != 1 && !getenv("B200BLUR_NO_TIGHT") && !getenv("B200BLUR_NO_TIGHT_OUT");
+    const bool repitch = row_bytes % 16 != 0 && channels <= 4 && row_bytes >= 256 && !one_pass;
     const size_t dev_pitch = repitch ? (row_bytes + 15) / 16 * 16 : row_bytes;
     const size_t dev_image_bytes = dev_pitch * (size_t)height;
     // rows up to 4 KB: the blur reads the tight upload as it is (TIGHT input), only the output is re-packed

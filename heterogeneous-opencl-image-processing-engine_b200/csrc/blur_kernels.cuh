@@ -238,6 +238,8 @@ struct StreamParams {
     int sstride;        // shared-memory row stride in bytes = cb*16 + 2*margin, or the row pitch when margin == 0
     int slot_bytes;     // ipc * RB * sstride (TIGHT: ipc * lane_bytes)
     int lane_bytes;     // TIGHT: shared-memory bytes of one image lane of a slot (16 B lead pad + up to 3 runs of rows + slack)
+    int stage_pitch;    // TIGHT output: row pitch of the shared-memory output staging (row bytes rounded up to 16)
+    int stage_slot_bytes;   // ... bytes of one staging slot = ipc * RB * stage_pitch
     long long img_blocks;   // ceil(n_images / ipc)
     // Guided tail: image blocks [0, ib_coarse) are cut into `nseg` segments of `seg` rows, the remaining image blocks --
     // the last work handed out -- into `nseg_fine` segments of `seg_fine` rows, so that the CTAs run dry within a
@@ -331,6 +333,20 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4 &v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 16 bytes at an arbitrary shared-memory byte address: five aligned words and four funnel shifts
+__device__ __forceinline__ uint4 lds_unaligned16(uint32_t a)
+{
+    const uint32_t a4 = a & ~3u, sh = (a & 3u) * 8u;
+    uint32_t x[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) x[i] = lds32(a4 + 4u * i);
+    return make_uint4(__funnelshift_r(x[0], x[1], sh), __funnelshift_r(x[1], x[2], sh), __funnelshift_r(x[2], x[3], sh),
+                      __funnelshift_r(x[3], x[4], sh));
 }
 // Programmatic dependent launch: the next kernel in the stream may start its prologue while this one drains
 // (launch_dependents), and must not touch global memory before the previous kernel has completed and flushed (wait).
@@ -524,11 +540,126 @@ constexpr int kFeedDepth = 8;   // group records in flight per CTA between produ
 // groups.  (A static round-robin persistent grid loses ~10 % of HBM bandwidth on B200 -- tools/membench.cu.)
 // EDGE = rows that do not end on a chunk boundary (pitched rows); compiled separately so the aligned case pays nothing.
 constexpr int kTightMaxLanes = 16;   // image lanes per group in TIGHT mode (rows >= 256 bytes, <= 256 consumer threads)
+constexpr int kStoreWarps = 4;       // TIGHT output: warps that flush the staged rows to (unaligned) global memory
+constexpr int kStageSlots = 2;       // ... output staging slots (one per input ring slot in flight between consumers and store warps)
+constexpr int kStageRecs = 8;        // ... slot records in flight between producer and store warps (>= NS + kStageSlots)
 
-template <int C, int RB, int NS, bool EDGE = false, bool FEED = false, bool TIGHT = false>
-__global__ void __launch_bounds__((FEED ? 64 : 32) + 256)
+// What a store warp needs to know about the output rows of one ring slot (written by the producer).
+struct __align__(16) StageRec {
+    uint8_t *out0;   // image lane 0: address of the slot's first output row (tight rows, any alignment)
+    int n_img;
+    int n_rows;      // output rows produced from this slot (0: nothing to flush)
+    int stop;        // 1: no more slots
+    int pad_[3];
+};
+static_assert(sizeof(StageRec) == 32, "StageRec is 32 bytes");
+
+// Bytes [first, last) of the 16-byte value v to the 16-byte aligned address p, in pieces aligned to their own size.
+__device__ __forceinline__ void store_bytes(uint8_t *p, const uint4 &v, int first, int last)
+{
+    int pos = first;
+    while (pos < last) {
+        const int align = pos ? (pos & -pos) : 16;
+        int sz = 8;
+        while (sz > align || sz > last - pos) sz >>= 1;
+        const int wi = pos >> 2;
+        const uint32_t w = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
+        if (sz == 8) {
+            const uint32_t w2 = wi == 0 ? v.y : v.w;
+            *reinterpret_cast<uint2 *>(p + pos) = make_uint2(w, w2);
+        } else if (sz == 4) {
+            *reinterpret_cast<uint32_t *>(p + pos) = w;
+        } else if (sz == 2) {
+            *reinterpret_cast<unsigned short *>(p + pos) = (unsigned short)(w >> (8 * (pos & 2)));
+        } else {
+            p[pos] = (uint8_t)(w >> (8 * (pos & 3)));
+        }
+        pos += sz;
+    }
+}
+
+// TIGHT output: the store warps write `n_rows` staged rows (shared memory, pitch `spitch`, 16-byte aligned) of one image
+// lane to the tight rows starting at the arbitrary byte address `g` -- one aligned 16-byte global word per lane and step,
+// words m = first, first + stride, ... of the span.  A word inside one row is one unaligned shared-memory read; a word
+// that straddles two rows is two reads merged with byte masks; the two words that stick out of the span are written in
+// narrower aligned pieces (the bytes next to them belong to another slot, possibly another CTA).  Three words are in
+// flight per lane (the reads of all three are issued before the first is used): a lone warp is latency-bound otherwise.
+__device__ __forceinline__ void flush_rows_tight(uint8_t *g, uint32_t stage_lane, int n_rows, int row_bytes, int spitch, int first_word,
+                                                 int word_stride)
+{
+    constexpr int U = 3;
+    const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+    const int head = (int)(ga & 15u);
+    uint8_t *w0 = g - head;
+    const int span = n_rows * row_bytes;
+    const int n_words = (head + span + 15) >> 4;
+    for (int m0 = first_word; m0 < n_words; m0 += U * word_stride) {
+        uint32_t addr[U], addr2[U];
+        int kk[U];          // > 0: the word straddles two rows, kk bytes come from the first
+        uint32_t x[U][5], y[U][5];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int m = m0 + u * word_stride;
+            const int b0 = 16 * m - head;
+            // row and column of the word's first valid byte (b0 itself for full words; clamped to the span for the two partial ones)
+            const int bb = b0 < 0 ? 0 : b0;
+            const unsigned r = (unsigned)bb / (unsigned)row_bytes;
+            const int col = b0 - (int)(r * (unsigned)row_bytes);
+            addr[u] = (uint32_t)((int)(stage_lane + r * (unsigned)spitch) + col);
+            const bool full = m < n_words && b0 >= 0 && b0 + 16 <= span;
+            kk[u] = (full && col + 16 > row_bytes) ? row_bytes - col : 0;
+            addr2[u] = stage_lane + (r + 1) * (unsigned)spitch - (unsigned)kk[u];
+            if (m >= n_words) addr[u] = stage_lane;   // past the end: harmless reads, no store
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t a4 = addr[u] & ~3u;
+#pragma unroll
+            for (int i = 0; i < 5; i++) x[u][i] = ptx::lds32(a4 + 4u * i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int m = m0 + u * word_stride;
+            if (m >= n_words) continue;
+            const int b0 = 16 * m - head;
+            const uint32_t sh = (addr[u] & 3u) * 8u;
+            uint4 v = make_uint4(__funnelshift_r(x[u][0], x[u][1], sh), __funnelshift_r(x[u][1], x[u][2], sh),
+                                 __funnelshift_r(x[u][2], x[u][3], sh), __funnelshift_r(x[u][3], x[u][4], sh));
+            uint8_t *dst = w0 + (size_t)m * 16;
+            if (b0 >= 0 && b0 + 16 <= span) {
+                if (kk[u] > 0) {   // straddles two rows (at most one word per row does)
+                    const uint32_t a4 = addr2[u] & ~3u, sh2 = (addr2[u] & 3u) * 8u;
+#pragma unroll
+                    for (int i = 0; i < 5; i++) y[u][i] = ptx::lds32(a4 + 4u * i);
+                    const uint32_t bw[4] = {__funnelshift_r(y[u][0], y[u][1], sh2), __funnelshift_r(y[u][1], y[u][2], sh2),
+                                            __funnelshift_r(y[u][2], y[u][3], sh2), __funnelshift_r(y[u][3], y[u][4], sh2)};
+                    const uint32_t aw[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int nb = kk[u] - 4 * i;
+                        const uint32_t mk = nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
+                        o[i] = (aw[i] & mk) | (bw[i] & ~mk);
+                    }
+                    v = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                stg128_stream(dst, v);
+            } else {
+                // first or last word of the span: all its valid bytes lie in one row (rows are >= 256 bytes)
+                store_bytes(dst, v, b0 < 0 ? -b0 : 0, span - b0 < 16 ? span - b0 : 16);
+            }
+        }
+    }
+}
+
+// TIGHT: 0 = 16-byte pitched/aligned rows on both sides; 1 = tight unaligned INPUT rows (re-aligned by the loads),
+// pitched output; 2 = tight unaligned input AND output rows: the consumers stage their (row-relative, aligned) output
+// chunks in shared memory and kStoreWarps extra warps write them out as aligned 16-byte global words.
+template <int C, int RB, int NS, bool EDGE = false, bool FEED = false, int TIGHT = 0>
+__global__ void __launch_bounds__((FEED ? 64 : TIGHT == 2 ? 32 + 32 * kStoreWarps : 32) + 256)
 blur_stream_kernel(const StreamParams sp)
 {
+    constexpr bool TOUT = TIGHT == 2;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // layout: [16 B pad][NS slots][16 B pad][NS full barriers][NS empty barriers][NS group records]
     const uint32_t ring = ptx::smem_u32(smem_raw) + 16;
@@ -541,8 +672,15 @@ blur_stream_kernel(const StreamParams sp)
     int2 *grec = reinterpret_cast<int2 *>(reinterpret_cast<uint8_t *>(meta + NS) + 16 * kFeedDepth);
     // TIGHT: [NS][kTightMaxLanes][RB] byte offsets of the rows of a slot within their image lane (after the group records)
     unsigned short *rowoff = reinterpret_cast<unsigned short *>(meta + NS);
+    // TIGHT output: [kStageSlots "staged" barriers][kStageSlots "flushed" barriers][kStageRecs slot records][16 B pad]
+    // [kStageSlots staging slots of ipc x RB rows]
+    uint8_t *tout_base = reinterpret_cast<uint8_t *>(rowoff + NS * kTightMaxLanes * RB);
+    const uint32_t ofull = ptx::smem_u32(tout_base);
+    const uint32_t oempty = ofull + 8 * kStageSlots;
+    StageRec *orec = reinterpret_cast<StageRec *>(tout_base + 16 * kStageSlots);
+    const uint32_t stage = ofull + 16 * kStageSlots + (uint32_t)sizeof(StageRec) * kStageRecs + 16;
     const int t = threadIdx.x;
-    constexpr int LEAD = FEED ? 64 : 32;   // threads before the consumers: producer warp (+ accountant warp)
+    constexpr int LEAD = FEED ? 64 : TOUT ? 32 + 32 * kStoreWarps : 32;   // threads before the consumers
     const int n_cwarps = ((int)blockDim.x - LEAD) >> 5;
     if (t == 0) {
         for (int i = 0; i < NS; i++) {
@@ -553,6 +691,11 @@ blur_stream_kernel(const StreamParams sp)
             for (int i = 0; i < kFeedDepth; i++) {
                 ptx::mbar_init(gdone + 8 * i, n_cwarps + 1);
                 ptx::mbar_init(gfree + 8 * i, 1);
+            }
+        if (TOUT)
+            for (int i = 0; i < kStageSlots; i++) {
+                ptx::mbar_init(ofull + 8 * i, n_cwarps);
+                ptx::mbar_init(oempty + 8 * i, kStoreWarps);
             }
         ptx::fence_barrier_init();
     }
@@ -594,6 +737,25 @@ blur_stream_kernel(const StreamParams sp)
                         else feed_count_arrivals(sp, rec[i].x, (unsigned int)rec[i].y, old[i], (unsigned)n_cwarps);
                     }
             }
+        }
+        return;
+    }
+    if (TOUT && t >= 32 && t < LEAD) {
+        // ------------------------------------------------------------------ store warps (TIGHT output only)
+        // For every ring slot the consumers finish, flush the rows they staged.
+        const int sw = (t >> 5) - 1, lane = t & 31;
+        for (unsigned j = 0;; j++) {
+            const int os = j % kStageSlots;
+            ptx::mbar_wait(ofull + 8 * os, (j / kStageSlots) & 1);
+            const StageRec rec = orec[j % kStageRecs];
+            if (rec.stop) break;
+            if (rec.n_rows > 0)
+                for (int il = 0; il < rec.n_img; il++)   // every store warp takes its share of every image lane's words
+                    flush_rows_tight(rec.out0 + (size_t)il * sp.b.out_stride,
+                                     stage + (uint32_t)(os * sp.stage_slot_bytes + il * RB * sp.stage_pitch), rec.n_rows,
+                                     sp.b.row_bytes, sp.stage_pitch, sw * 32 + lane, 32 * kStoreWarps);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(oempty + 8 * os);   // the staging slot may be overwritten
         }
         return;
     }
@@ -699,6 +861,17 @@ blur_stream_kernel(const StreamParams sp)
                     // wait until every consumer warp has released this buffer (passes at once on first use)
                     ptx::mbar_wait(empty + 8 * buf, ((pcount / NS) & 1) ^ 1);
                     if (s == 0) meta[buf] = m;
+                    if (TOUT) {
+                        // what the store warps will flush for this slot: output row k-2 comes from input row k >= 2
+                        StageRec rec;
+                        const int k0 = s * RB, k1 = done ? 0 : min(k0 + RB, q.nr + 2), kf = k0 > 2 ? k0 : 2;
+                        rec.out0 = done ? nullptr : m.out + (size_t)(kf - 2) * (size_t)sp.b.out_pitch;
+                        rec.n_img = done ? 0 : q.n_img;
+                        rec.n_rows = k1 > kf ? k1 - kf : 0;
+                        rec.stop = done ? 1 : 0;
+                        rec.pad_[0] = rec.pad_[1] = rec.pad_[2] = 0;
+                        orec[pcount % kStageRecs] = rec;
+                    }
                     if (done) ptx::mbar_arrive(full + 8 * buf);   // sentinel slot: no data, tells the consumers to stop
                     else if (TIGHT)
                         stream_issue_slot_tight<RB>(sp, q, s, ring + (uint32_t)(buf * sp.slot_bytes), full + 8 * buf,
@@ -728,7 +901,14 @@ blur_stream_kernel(const StreamParams sp)
         // the first slot of an item carries the group record
         ptx::mbar_wait(full + 8 * (ccount % NS), (ccount / NS) & 1);
         const GroupMeta m = meta[ccount % NS];
-        if (m.n_img < 0) break;
+        if (m.n_img < 0) {
+            if (TOUT) {   // pass the stop record on to the store warps
+                ptx::mbar_wait(oempty + 8 * (ccount % kStageSlots), ((ccount / kStageSlots) & 1) ^ 1);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ofull + 8 * (ccount % kStageSlots));
+            }
+            break;
+        }
         const bool active = (il < m.n_img) && (c < m.cbe);
         const bool first = (m.flags & 1) && (c == 0);
         const bool last = (m.flags & 2) && (c == m.cbe - 1);               // the chunk that holds the end of the row
@@ -790,7 +970,10 @@ blur_stream_kernel(const StreamParams sp)
             o.y = __byte_perm(v[2], v[3], 0x7351);
             o.z = __byte_perm(v[4], v[5], 0x7351);
             o.w = __byte_perm(v[6], v[7], 0x7351);
-            if (store) stg128_stream(out_row, o);
+            if (store) {
+                if (!TOUT) stg128_stream(out_row, o);
+                else ptx::sts128((uint32_t)reinterpret_cast<uintptr_t>(out_row), o);   // out_row = staging address (TIGHT output)
+            }
         };
         const int k_end = m.nr + 2;
         int k = 0;  // input-row index within the item
@@ -803,26 +986,39 @@ blur_stream_kernel(const StreamParams sp)
             auto row_addr = [&](int r) -> uint32_t {
                 return TIGHT ? a + (uint32_t)ro[r] : a + (uint32_t)r * (uint32_t)sp.sstride;
             };
+            if (TOUT) {
+                // this slot's output goes to staging slot ccount % kStageSlots, once the store warps are done with it;
+                // the row produced from input row k of the group lands in staging row k - max(first k of the slot, 2)
+                const int os = ccount % kStageSlots;
+                ptx::mbar_wait(oempty + 8 * os, ((ccount / kStageSlots) & 1) ^ 1);
+                const int kf = k > 2 ? k : 2;
+                dst = reinterpret_cast<uint8_t *>((uintptr_t)(stage + (uint32_t)(os * sp.stage_slot_bytes) +
+                                                              (uint32_t)((il_c * RB + (k - kf)) * sp.stage_pitch + c_c * 16)));
+            }
             // Whole slots (the planner sizes groups so that nearly all are) run fully unrolled with compile-time row
             // offsets and no per-row trip test; the first slot of a group only differs in not storing rows 0 and 1.
+            const size_t out_step = TOUT ? (size_t)sp.stage_pitch : (size_t)sp.b.out_pitch;
             if (k_end - k >= RB) {
                 if (s == 0) {
 #pragma unroll
-                    for (int r = 0; r < RB; r++) row(row_addr(r), dst + (size_t)r * (size_t)sp.b.out_pitch, active && r >= 2);
+                    for (int r = 0; r < RB; r++) row(row_addr(r), dst + (size_t)r * out_step, active && r >= 2);
                 } else {
 #pragma unroll
-                    for (int r = 0; r < RB; r++) row(row_addr(r), dst + (size_t)r * (size_t)sp.b.out_pitch, active);
+                    for (int r = 0; r < RB; r++) row(row_addr(r), dst + (size_t)r * out_step, active);
                 }
                 k += RB;
             } else {
                 const int n = k_end - k;                // short last slot of a group (uniform across the CTA)
 #pragma unroll 1
-                for (int r = 0; r < n; r++) row(row_addr(r), dst + (size_t)r * (size_t)sp.b.out_pitch, active && k + r >= 2);
+                for (int r = 0; r < n; r++) row(row_addr(r), dst + (size_t)r * out_step, active && k + r >= 2);
                 k += n;
             }
-            dst += (size_t)RB * (size_t)sp.b.out_pitch;
+            dst += (size_t)RB * out_step;
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(empty + 8 * buf);   // this warp is done reading the slot
+            if (lane == 0) {
+                ptx::mbar_arrive(empty + 8 * buf);   // this warp is done reading the slot
+                if (TOUT) ptx::mbar_arrive(ofull + 8 * (ccount % kStageSlots));   // ... and has staged its output rows
+            }
         }
         if (FEED) {
             // this warp's stores of the group are issued: arrive (release, CTA scope) for the accountant
