@@ -144,3 +144,17 @@ def test_cli_blurs_a_jpeg_input(tmp_path, name):
                 "--quiet"], str(tmp_path))
     assert "Total images processed: 50" in text
     assert np.array_equal(read_ppm(out_path), want)
+
+
+@pytest.mark.parametrize("prog,args", [("heterogeneous_blur", ["both", "0.5", "9"]), ("split_image_blur", ["0.6", "9"])])
+def test_clis_on_an_odd_width_image(tmp_path, prog, args):
+    """A 251x97 image (753-byte rows: neither 16-byte multiples nor aligned from row to row) through both CLIs on three
+    workers: the tight-row kernel (unaligned loads, store warps) under Approach 1 shards and under Approach 2 bands whose
+    halo rows are read through the neighbours' buffers."""
+    img = np.random.default_rng(77).integers(0, 256, size=(97, 251, 3), dtype=np.uint8)
+    src, out_path = os.path.join(tmp_path, "odd.ppm"), os.path.join(tmp_path, "odd_out.ppm")
+    write_ppm(src, img)
+    text = run([os.path.join(BIN, prog)] + args + ["--images", "120", "--gpus", "3", "--oversubscribe", "--input", src, "--save",
+                                                   out_path, "--quiet"], str(tmp_path))
+    assert "Total images processed: 120" in text
+    assert np.array_equal(read_ppm(out_path), oracle.c_blur(img))
