@@ -411,7 +411,7 @@ int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, Str
         sp.ipc = 1;
     }
     // TIGHT: an image lane of a slot = 16 B lead pad + up to three runs of rows, each widened to 16-byte boundaries
-    sp.lane_bytes = tight ? (cfg.rb * p.row_bytes + 15) / 16 * 16 + 128 : 0;
+    sp.lane_bytes = tight ? (cfg.rb * p.pitch + 15) / 16 * 16 + 128 : 0;
     sp.stage_pitch = tight == 2 ? (p.row_bytes + 15) / 16 * 16 : 0;
     auto smem_for = [&](int ipc) {
         const int sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;
@@ -426,6 +426,7 @@ int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, Str
     sp.sstride = sp.margin ? sp.cb * 16 + 2 * sp.margin : p.pitch;   // whole rows land exactly as they lie in memory
     sp.slot_bytes = tight ? sp.ipc * sp.lane_bytes : sp.ipc * cfg.rb * sp.sstride;
     sp.stage_slot_bytes = sp.ipc * cfg.rb * sp.stage_pitch;
+    sp.row_recip = p.row_bytes > 1 ? (unsigned)((0x100000000ULL + (unsigned)p.row_bytes - 1) / (unsigned)p.row_bytes) : 0u;
     plan.smem = smem_for(sp.ipc);
     plan.block = threads + (feed ? 64 : tight == 2 ? 32 + 32 * b200blur::kStoreWarps : 32);  // + producer (+ accountant / store warps)
     if (plan.smem > 220 * 1024) return fail(B200BLUR_ERR_INVALID, "streamed kernel needs %zu B of shared memory", plan.smem);

@@ -240,6 +240,7 @@ struct StreamParams {
     int lane_bytes;     // TIGHT: shared-memory bytes of one image lane of a slot (16 B lead pad + up to 3 runs of rows + slack)
     int stage_pitch;    // TIGHT output: row pitch of the shared-memory output staging (row bytes rounded up to 16)
     int stage_slot_bytes;   // ... bytes of one staging slot = ipc * RB * stage_pitch
+    unsigned row_recip;     // ... ceil(2^32 / row_bytes): offset / row_bytes == umulhi(offset, row_recip) for offsets < 2^16
     long long img_blocks;   // ceil(n_images / ipc)
     // Guided tail: image blocks [0, ib_coarse) are cut into `nseg` segments of `seg` rows, the remaining image blocks --
     // the last work handed out -- into `nseg_fine` segments of `seg_fine` rows, so that the CTAs run dry within a
@@ -458,7 +459,8 @@ __device__ __forceinline__ void stream_issue_slot_tight(const StreamParams &sp, 
                 run = min(k1 - k, b.rows - j);
             }
             const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(rp) & 15u);
-            const uint32_t bytes = (delta + (uint32_t)run * (uint32_t)b.row_bytes + 15u) & ~15u;
+            // (rows of a run are b.pitch apart: the tight case pitch == row_bytes, or any other unaligned pitch)
+            const uint32_t bytes = (delta + (uint32_t)(run - 1) * (uint32_t)b.pitch + (uint32_t)b.row_bytes + 15u) & ~15u;
             for (int i = 0; i < run; i++)
                 rowoff[il * RB + (k - k0) + i] = (unsigned short)(cur + delta + (uint32_t)i * (uint32_t)b.pitch);
             ptx::mbar_expect_tx(bar, bytes);
@@ -584,8 +586,8 @@ __device__ __forceinline__ void store_bytes(uint8_t *p, const uint4 &v, int firs
 // that straddles two rows is two reads merged with byte masks; the two words that stick out of the span are written in
 // narrower aligned pieces (the bytes next to them belong to another slot, possibly another CTA).  Three words are in
 // flight per lane (the reads of all three are issued before the first is used): a lone warp is latency-bound otherwise.
-__device__ __forceinline__ void flush_rows_tight(uint8_t *g, uint32_t stage_lane, int n_rows, int row_bytes, int spitch, int first_word,
-                                                 int word_stride)
+__device__ __forceinline__ void flush_rows_tight(uint8_t *g, uint32_t stage_lane, int n_rows, int row_bytes, unsigned row_recip,
+                                                 int spitch, int first_word, int word_stride)
 {
     constexpr int U = 3;
     const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
@@ -603,7 +605,7 @@ __device__ __forceinline__ void flush_rows_tight(uint8_t *g, uint32_t stage_lane
             const int b0 = 16 * m - head;
             // row and column of the word's first valid byte (b0 itself for full words; clamped to the span for the two partial ones)
             const int bb = b0 < 0 ? 0 : b0;
-            const unsigned r = (unsigned)bb / (unsigned)row_bytes;
+            const unsigned r = __umulhi((unsigned)bb, row_recip);   // bb / row_bytes (a slot's span is < 2^16 bytes)
             const int col = b0 - (int)(r * (unsigned)row_bytes);
             addr[u] = (uint32_t)((int)(stage_lane + r * (unsigned)spitch) + col);
             const bool full = m < n_words && b0 >= 0 && b0 + 16 <= span;
@@ -753,7 +755,7 @@ blur_stream_kernel(const StreamParams sp)
                 for (int il = 0; il < rec.n_img; il++)   // every store warp takes its share of every image lane's words
                     flush_rows_tight(rec.out0 + (size_t)il * sp.b.out_stride,
                                      stage + (uint32_t)(os * sp.stage_slot_bytes + il * RB * sp.stage_pitch), rec.n_rows,
-                                     sp.b.row_bytes, sp.stage_pitch, sw * 32 + lane, 32 * kStoreWarps);
+                                     sp.b.row_bytes, sp.row_recip, sp.stage_pitch, sw * 32 + lane, 32 * kStoreWarps);
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(oempty + 8 * os);   // the staging slot may be overwritten
         }

@@ -422,6 +422,27 @@ def test_tight_row_bands_with_halo_pointers(ctx, h, w, g):
     assert_same(_run_launch(ctx, x, launches), want)
 
 
+@pytest.mark.parametrize("w,c,in_pitch", [(250, 3, 777), (100, 3, 301), (130, 2, 1000), (320, 3, 963)])
+def test_input_rows_with_an_unaligned_pitch(ctx, w, c, in_pitch):
+    """Input rows padded to a pitch that is not a multiple of 16 (a view into a wider tight image): read as they are."""
+    n, h = 3, 21
+    P = w * c
+    x = synth(w + in_pitch, n, h, w, c)
+    padded = np.full((n, h, in_pitch), 0x5A, np.uint8)
+    padded[:, :, :P] = x.reshape(n, h, P)
+    pitch_out = (P + 15) // 16 * 16
+    d_in, d_out = ctx.dev_alloc(padded.nbytes + 64), ctx.dev_alloc(n * h * pitch_out + 64)
+    ctx.enqueue_write(0, d_in + 1, padded, padded.nbytes)
+    l = ctx.launch_rows(d_in + 1, d_out, w, h, c, 0, h, n, in_row_pitch=in_pitch, out_row_pitch=pitch_out)
+    ctx.enqueue_blur(0, l)
+    out = np.zeros_like(x)
+    ctx.enqueue_read_2d(0, out, P, d_out, pitch_out, P, n * h)
+    ctx.finish()
+    ctx.dev_free(d_in)
+    ctx.dev_free(d_out)
+    assert_same(out, oracle.c_blur_batch(x))
+
+
 def test_misaligned_input_with_aligned_row_length(ctx):
     """width*channels a multiple of 16 but the input pointer is not 16-byte aligned (a view into a larger buffer)."""
     x = synth(99, 4, 30, 320, 3)
