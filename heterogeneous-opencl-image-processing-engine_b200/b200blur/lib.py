@@ -8,7 +8,7 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_in
                     c_void_p, create_string_buffer)
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_LIB = os.path.join(_PKG_DIR, "libb200blur.so")
+_LIB = os.environ.get("B200BLUR_LIB") or os.path.join(_PKG_DIR, "libb200blur.so")   # (B200BLUR_LIB: A/B builds of the library)
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_PEER = 0, -1, -2, -3, -4, -5
 IPC_HANDLE_BYTES = 64

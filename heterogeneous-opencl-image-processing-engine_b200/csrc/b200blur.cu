@@ -419,7 +419,7 @@ int plan_stream(b200blur_ctx *ctx, const b200blur::BandParams &p, bool feed, Str
         return 16 + (size_t)cfg.ns * slot + 16 + 16 * cfg.ns + sizeof(b200blur::GroupMeta) * cfg.ns +
                (feed ? 24 * b200blur::kFeedDepth : 0) + (tight ? 2 * cfg.ns * b200blur::kTightMaxLanes * cfg.rb : 0) +
                (tight == 2 ? 16 * b200blur::kStageSlots + sizeof(b200blur::StageRec) * b200blur::kStageRecs + 16 +
-                                 (size_t)b200blur::kStageSlots * ipc * cfg.rb * sp.stage_pitch + 16
+                                 (size_t)b200blur::kStageSlots * ipc * cfg.rb * sp.stage_pitch + 32
                            : 0);
     };
     while (sp.ipc > 1 && smem_for(sp.ipc) > 200 * 1024) sp.ipc--;   // fewer images side by side rather than no launch

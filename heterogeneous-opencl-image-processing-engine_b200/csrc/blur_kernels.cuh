@@ -542,8 +542,14 @@ constexpr int kFeedDepth = 8;   // group records in flight per CTA between produ
 // groups.  (A static round-robin persistent grid loses ~10 % of HBM bandwidth on B200 -- tools/membench.cu.)
 // EDGE = rows that do not end on a chunk boundary (pitched rows); compiled separately so the aligned case pays nothing.
 constexpr int kTightMaxLanes = 16;   // image lanes per group in TIGHT mode (rows >= 256 bytes, <= 256 consumer threads)
-constexpr int kStoreWarps = 4;       // TIGHT output: warps that flush the staged rows to (unaligned) global memory
-constexpr int kStageSlots = 2;       // ... output staging slots (one per input ring slot in flight between consumers and store warps)
+#ifndef B200BLUR_STORE_WARPS
+#define B200BLUR_STORE_WARPS 4
+#endif
+#ifndef B200BLUR_STAGE_SLOTS
+#define B200BLUR_STAGE_SLOTS 2
+#endif
+constexpr int kStoreWarps = B200BLUR_STORE_WARPS;       // TIGHT output: warps that flush the staged rows to (unaligned) global memory
+constexpr int kStageSlots = B200BLUR_STAGE_SLOTS;       // ... output staging slots (one per input ring slot in flight between consumers and store warps)
 constexpr int kStageRecs = 8;        // ... slot records in flight between producer and store warps (>= NS + kStageSlots)
 
 // What a store warp needs to know about the output rows of one ring slot (written by the producer).
@@ -582,75 +588,41 @@ __device__ __forceinline__ void store_bytes(uint8_t *p, const uint4 &v, int firs
 
 // TIGHT output: the store warps write `n_rows` staged rows (shared memory, pitch `spitch`, 16-byte aligned) of one image
 // lane to the tight rows starting at the arbitrary byte address `g` -- one aligned 16-byte global word per lane and step,
-// words m = first, first + stride, ... of the span.  A word inside one row is one unaligned shared-memory read; a word
-// that straddles two rows is two reads merged with byte masks; the two words that stick out of the span are written in
-// narrower aligned pieces (the bytes next to them belong to another slot, possibly another CTA).  Three words are in
-// flight per lane (the reads of all three are issued before the first is used): a lone warp is latency-bound otherwise.
+// words m = first, first + stride, ... of the span.  Every word is built the same way, without divergence: two unaligned
+// shared-memory reads -- the row that holds the word's first byte, and the next row read `k` bytes early so that its
+// bytes sit at the same positions -- merged with byte masks (k = 16 for the words that lie inside one row, which then
+// take everything from the first read).  Only the two words that stick out of the span (their other bytes belong to
+// another slot, possibly another CTA) are written in narrower aligned pieces.
 __device__ __forceinline__ void flush_rows_tight(uint8_t *g, uint32_t stage_lane, int n_rows, int row_bytes, unsigned row_recip,
                                                  int spitch, int first_word, int word_stride)
 {
-    constexpr int U = 3;
     const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
     const int head = (int)(ga & 15u);
     uint8_t *w0 = g - head;
     const int span = n_rows * row_bytes;
     const int n_words = (head + span + 15) >> 4;
-    for (int m0 = first_word; m0 < n_words; m0 += U * word_stride) {
-        uint32_t addr[U], addr2[U];
-        int kk[U];          // > 0: the word straddles two rows, kk bytes come from the first
-        uint32_t x[U][5], y[U][5];
+    for (int m = first_word; m < n_words; m += word_stride) {
+        const int b0 = 16 * m - head;
+        const int bb = b0 < 0 ? 0 : b0;                              // first valid byte (b0 itself except for the first word)
+        const unsigned r = __umulhi((unsigned)bb, row_recip);        // bb / row_bytes (a slot's span is < 2^16 bytes)
+        const int col = b0 - (int)(r * (unsigned)row_bytes);         // may be negative for the first word
+        int k = row_bytes - col;                                     // bytes of the word that row r holds
+        k = k > 16 ? 16 : k;
+        const uint32_t a1 = (uint32_t)((int)(stage_lane + r * (unsigned)spitch) + col);
+        const uint32_t a2 = k < 16 ? stage_lane + (r + 1) * (unsigned)spitch - (unsigned)k : a1;
+        const uint4 va = ptx::lds_unaligned16(a1), vb = ptx::lds_unaligned16(a2);
+        const uint32_t aw[4] = {va.x, va.y, va.z, va.w}, bw[4] = {vb.x, vb.y, vb.z, vb.w};
+        uint32_t o[4];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int m = m0 + u * word_stride;
-            const int b0 = 16 * m - head;
-            // row and column of the word's first valid byte (b0 itself for full words; clamped to the span for the two partial ones)
-            const int bb = b0 < 0 ? 0 : b0;
-            const unsigned r = __umulhi((unsigned)bb, row_recip);   // bb / row_bytes (a slot's span is < 2^16 bytes)
-            const int col = b0 - (int)(r * (unsigned)row_bytes);
-            addr[u] = (uint32_t)((int)(stage_lane + r * (unsigned)spitch) + col);
-            const bool full = m < n_words && b0 >= 0 && b0 + 16 <= span;
-            kk[u] = (full && col + 16 > row_bytes) ? row_bytes - col : 0;
-            addr2[u] = stage_lane + (r + 1) * (unsigned)spitch - (unsigned)kk[u];
-            if (m >= n_words) addr[u] = stage_lane;   // past the end: harmless reads, no store
+        for (int i = 0; i < 4; i++) {
+            const int nb = k - 4 * i;
+            const uint32_t mk = nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
+            o[i] = (aw[i] & mk) | (bw[i] & ~mk);
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t a4 = addr[u] & ~3u;
-#pragma unroll
-            for (int i = 0; i < 5; i++) x[u][i] = ptx::lds32(a4 + 4u * i);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int m = m0 + u * word_stride;
-            if (m >= n_words) continue;
-            const int b0 = 16 * m - head;
-            const uint32_t sh = (addr[u] & 3u) * 8u;
-            uint4 v = make_uint4(__funnelshift_r(x[u][0], x[u][1], sh), __funnelshift_r(x[u][1], x[u][2], sh),
-                                 __funnelshift_r(x[u][2], x[u][3], sh), __funnelshift_r(x[u][3], x[u][4], sh));
-            uint8_t *dst = w0 + (size_t)m * 16;
-            if (b0 >= 0 && b0 + 16 <= span) {
-                if (kk[u] > 0) {   // straddles two rows (at most one word per row does)
-                    const uint32_t a4 = addr2[u] & ~3u, sh2 = (addr2[u] & 3u) * 8u;
-#pragma unroll
-                    for (int i = 0; i < 5; i++) y[u][i] = ptx::lds32(a4 + 4u * i);
-                    const uint32_t bw[4] = {__funnelshift_r(y[u][0], y[u][1], sh2), __funnelshift_r(y[u][1], y[u][2], sh2),
-                                            __funnelshift_r(y[u][2], y[u][3], sh2), __funnelshift_r(y[u][3], y[u][4], sh2)};
-                    const uint32_t aw[4] = {v.x, v.y, v.z, v.w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int nb = kk[u] - 4 * i;
-                        const uint32_t mk = nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
-                        o[i] = (aw[i] & mk) | (bw[i] & ~mk);
-                    }
-                    v = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-                stg128_stream(dst, v);
-            } else {
-                // first or last word of the span: all its valid bytes lie in one row (rows are >= 256 bytes)
-                store_bytes(dst, v, b0 < 0 ? -b0 : 0, span - b0 < 16 ? span - b0 : 16);
-            }
-        }
+        const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
+        uint8_t *dst = w0 + (size_t)m * 16;
+        if (b0 >= 0 && b0 + 16 <= span) stg128_stream(dst, v);
+        else store_bytes(dst, v, b0 < 0 ? -b0 : 0, span - b0 < 16 ? span - b0 : 16);   // first / last word of the span
     }
 }
 

@@ -31,26 +31,25 @@ def flush_rows_tight(mem, written, g, stage, stage_lane, n_rows, row_bytes, spit
     w0 = g - head
     span = n_rows * row_bytes
     n_words = (head + span + 15) >> 4
-    for m in range(n_words):                              # (lanes take m, m+32, ...: order does not matter)
+    recip = (2 ** 32 + row_bytes - 1) // row_bytes
+    for m in range(n_words):                              # (lanes take m, m + stride, ...: order does not matter)
         b0 = 16 * m - head
+        bb = max(b0, 0)
+        r = (bb * recip) >> 32                            # __umulhi(bb, row_recip)
+        assert r == bb // row_bytes
+        col = b0 - r * row_bytes
+        k = min(row_bytes - col, 16)
+        a1 = stage_lane + r * spitch + col
+        a2 = stage_lane + (r + 1) * spitch - k if k < 16 else a1
+        va, vb = lds_unaligned16(stage, a1), lds_unaligned16(stage, a2)
+        v = np.concatenate([va[:k], vb[k:]])              # byte-mask merge
         dst = w0 + 16 * m
         if b0 >= 0 and b0 + 16 <= span:
-            r, col = divmod(b0, row_bytes)
-            v = lds_unaligned16(stage, stage_lane + r * spitch + col)
-            if col + 16 > row_bytes:
-                k = row_bytes - col
-                b = lds_unaligned16(stage, stage_lane + (r + 1) * spitch - k)
-                v = np.concatenate([v[:k], b[k:]])
             assert dst % 16 == 0
             mem[dst:dst + 16] = v
             written[dst:dst + 16] += 1
         else:
-            first = -b0 if b0 < 0 else 0
-            last = span - b0 if span - b0 < 16 else 16
-            r = (b0 + first) // row_bytes
-            col = b0 - r * row_bytes
-            v = lds_unaligned16(stage, stage_lane + r * spitch + col)
-            store_bytes(mem, written, dst, v, first, last)
+            store_bytes(mem, written, dst, v, -b0 if b0 < 0 else 0, span - b0 if span - b0 < 16 else 16)
 
 
 @pytest.mark.parametrize("row_bytes", [256, 257, 258, 263, 300, 750, 1023, 4095])
@@ -60,7 +59,7 @@ def test_flush_writes_exactly_the_span(row_bytes, n_rows):
     spitch = (row_bytes + 15) // 16 * 16
     for align in range(16):
         rows = rng.integers(0, 256, size=(n_rows, row_bytes), dtype=np.uint8)
-        stage = rng.integers(0, 256, size=64 + n_rows * spitch + 64, dtype=np.uint8)   # garbage in the padding
+        stage = rng.integers(0, 256, size=64 + (n_rows + 1) * spitch + 64, dtype=np.uint8)   # garbage in the padding
         stage_lane = 64
         for r in range(n_rows):
             stage[stage_lane + r * spitch:stage_lane + r * spitch + row_bytes] = rows[r]
