@@ -123,14 +123,14 @@ def test_vectorised_path_selection():
     assert b200blur.Context.is_vectorised(mk(0x1000, 0x9000, 256, 256, 3, 0, 256, 4))
     assert b200blur.Context.is_vectorised(mk(0x1000, 0x9000, 16, 4, 1, 0, 4, 1))
     assert not b200blur.Context.is_vectorised(mk(0x1000, 0x9000, 17, 33, 3, 0, 33, 1))      # pitch % 16 != 0
-    # an unaligned INPUT pointer is fine since round 2 (rows >= 256 bytes: aligned-superset copies, re-aligned in shared
-    # memory); an unaligned OUTPUT pointer, or a short unaligned row, still is not
-    assert b200blur.Context.is_vectorised(mk(0x1004, 0x9000, 256, 256, 3, 0, 256, 1))
-    assert not b200blur.Context.is_vectorised(mk(0x1000, 0x9004, 256, 256, 3, 0, 256, 1))
-    assert not b200blur.Context.is_vectorised(mk(0x1004, 0x9000, 16, 4, 1, 0, 4, 1))
-    # tight odd-width input with a 16-byte pitched output
+    # round 2: tight rows of 256..4096 bytes run on the streamed kernel whatever their length and alignment, on either
+    # side (aligned-superset copies re-aligned in shared memory; store warps); short unaligned rows still do not
+    assert b200blur.Context.is_vectorised(mk(0x1004, 0x9000, 256, 256, 3, 0, 256, 1))       # unaligned input pointer
+    assert b200blur.Context.is_vectorised(mk(0x1000, 0x9004, 256, 256, 3, 0, 256, 1))       # unaligned output pointer
+    assert b200blur.Context.is_vectorised(mk(0x1000, 0x9000, 250, 37, 3, 0, 37, 2))         # odd width, tight both sides
     assert b200blur.Context.is_vectorised(mk(0x1000, 0x9000, 250, 37, 3, 0, 37, 2, 250 * 37 * 3, 752 * 37, 0, 752))
-    assert not b200blur.Context.is_vectorised(mk(0x1000, 0x9000, 250, 37, 3, 0, 37, 2))      # tight odd-width output
+    assert not b200blur.Context.is_vectorised(mk(0x1004, 0x9000, 16, 4, 1, 0, 4, 1))        # 16-byte rows, unaligned
+    assert not b200blur.Context.is_vectorised(mk(0x1000, 0x9000, 1366, 8, 3, 0, 8, 1))      # 4098-byte odd rows: too wide
     assert not b200blur.Context.is_vectorised(mk(0x1000, 0x9000, 16, 4, 5, 0, 4, 1))        # channels > 4
     assert not b200blur.Context.is_vectorised(mk(0x1000, 0x9000, 16, 4, 3, 0, 4, 2, 16 * 4 * 3 + 4, 192))
 
