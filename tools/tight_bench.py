@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""tools/tight_bench.py -- kernel-only timing of the streamed kernel on odd-width images: tight unaligned input rows
+(TIGHT input form) vs the same rows re-pitched to a multiple of 16 bytes, both with a 16-byte-pitched output."""
 import sys, os, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "heterogeneous-opencl-image-processing-engine_b200")):
