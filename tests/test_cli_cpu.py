@@ -64,3 +64,26 @@ def test_split_image_blur_banner_and_arguments():
     t = run([os.path.join(BIN, "split_image_blur"), "-3", "99999"]).stdout
     assert "Warning: gpu_ratio must be between 0.0 and 1.0. Using 0.5" in t
     assert "Warning: BATCH_SIZE must be between 1 and 5000. Using 500" in t
+
+
+@pytest.mark.parametrize("prog", ["heterogeneous_blur", "split_image_blur"])
+def test_trailing_options_are_parsed_after_the_reference_positionals(prog, tmp_path):
+    """The options that follow the reference's positional arguments (they only expose what the reference hard-codes, plus
+    the multi-GPU knobs of round 2) are accepted, bad values are refused, and a JPEG --input is decoded before the
+    device is looked for."""
+    pos = ["both", "0.5", "7"] if prog == "heterogeneous_blur" else ["0.5", "7"]
+    exe = os.path.join(BIN, prog)
+    jpg = os.path.join(ROOT, "tests", "golden", "jpeg", "420_q90_64x48.jpg")
+    ok = run([exe] + pos + ["--images", "21", "--gpus", "3", "--oversubscribe", "--ring", "2", "--fuse", "1", "--fill-threads", "2",
+                            "--static-split", "--quiet", "--checksum", "--input", jpg])
+    assert "Error: unknown option" not in ok.stdout and "Error: bad size option" not in ok.stdout
+    assert "Original image loaded: 64x48, 3 channels" in ok.stdout and "Number of batches: 3" in ok.stdout
+    if no_gpu():
+        assert ok.returncode == 255 and "Could not find a CUDA device" in ok.stdout
+    for bad in (["--ring", "1"], ["--ring", "65"], ["--images", "0"], ["--width", "-5"], ["--repeat", "0"], ["--nonsense"]):
+        out = run([exe] + pos + bad)
+        assert out.returncode == 255 and "Error:" in out.stdout
+    missing = run([exe] + pos + ["--input", os.path.join(str(tmp_path), "nothing.jpg")])
+    assert missing.returncode == 255 and "cannot read image file" in missing.stdout
+    progressive = run([exe] + pos + ["--input", os.path.join(ROOT, "tests", "golden", "jpeg", "progressive_32x24.jpg")])
+    assert progressive.returncode == 255 and "not supported" in progressive.stdout

@@ -87,3 +87,74 @@ def test_slot_records_cover_a_group():
             assert kf - 2 == pos or n_rows == 0
             pos += n_rows
         assert pos == nr
+
+
+# ---------------------------------------------------------------------------------------------- TIGHT input side
+def issue_slot_tight(mem, base, rows, row_bytes, pitch, first_row, n_slot_rows, top=None, bot=None, RB=8):
+    """The producer's side (stream_issue_slot_tight): one image lane of one ring slot.  Input rows first_row-1 ...
+    (row -1 / row `rows` = the halo rows `top` / `bot`, or the replicated edge row) are copied run by run as ALIGNED
+    SUPERSETS: the copy starts at the 16-byte boundary below the run's first byte and ends at the one above its last.
+    -> (lane bytes, rowoff[]) where rowoff[i] = offset of slot row i's first byte within the lane."""
+    lane = np.full(RB * pitch + 16 + 128, 0xCC, np.uint8)
+    rowoff = []
+    cur = 0
+    k = 0
+    while k < n_slot_rows:
+        j = first_row - 1 + k
+        run = 1
+        if j < 0:
+            rp = top if top is not None else base
+        elif j >= rows:
+            rp = bot if bot is not None else base + (rows - 1) * pitch
+        else:
+            rp = base + j * pitch
+            run = min(n_slot_rows - k, rows - j)
+        delta = rp & 15
+        nbytes = (delta + (run - 1) * pitch + row_bytes + 15) & ~15
+        assert (rp - delta) % 16 == 0 and nbytes % 16 == 0 and cur % 16 == 0      # what a bulk copy needs
+        assert nbytes - (delta + (run - 1) * pitch + row_bytes) < 16 and delta < 16   # never more than 15 extra bytes per end
+        lane[16 + cur:16 + cur + nbytes] = mem[rp - delta:rp - delta + nbytes]
+        for i in range(run):
+            rowoff.append(cur + delta + i * pitch)
+        cur += nbytes
+        k += run
+    assert 16 + cur <= len(lane)
+    return lane, rowoff
+
+
+def window(lane, a):
+    """The consumer's 24-byte window {wl, w, wr} at byte address a - 4: seven aligned words, six funnel shifts."""
+    a4 = (a - 4) & ~3
+    sh = (a - 4) & 3
+    x = lane[a4:a4 + 28]
+    return x[sh:sh + 24].copy()
+
+
+@pytest.mark.parametrize("row_bytes,pitch", [(750, 750), (257, 257), (300, 300), (4095, 4095), (750, 777), (256, 301)])
+@pytest.mark.parametrize("base_align", [0, 1, 7, 13])
+def test_tight_input_rows_land_where_the_consumers_look(row_bytes, pitch, base_align):
+    rng = np.random.default_rng(row_bytes + pitch + base_align)
+    rows = 21
+    base = 4096 + base_align
+    mem = rng.integers(0, 256, size=base + rows * pitch + 4096, dtype=np.uint8)
+    top_at, bot_at = 64 + 5, 2048 + 11                       # halo rows somewhere else, at their own alignment
+    for first_row, n_slot_rows, top, bot in [(0, 8, None, None), (0, 8, top_at, None), (5, 8, None, None), (14, 8, None, bot_at),
+                                             (14, 8, None, None), (20, 3, top_at, bot_at), (1, 2, None, None)]:
+        lane, rowoff = issue_slot_tight(mem, base, rows, row_bytes, pitch, first_row, n_slot_rows, top, bot)
+        assert len(rowoff) == n_slot_rows and max(rowoff) + row_bytes + 20 <= len(lane) - 16 + 16
+        for i, off in enumerate(rowoff):
+            j = first_row - 1 + i
+            if j < 0:
+                src = top if top is not None else base
+            elif j >= rows:
+                src = bot if bot is not None else base + (rows - 1) * pitch
+            else:
+                src = base + j * pitch
+            want = mem[src:src + row_bytes]
+            assert np.array_equal(lane[16 + off:16 + off + row_bytes], want)
+            for c in (0, 1, (row_bytes - 1) // 16):            # first chunks and the chunk that holds the end of the row
+                w = window(lane, 16 + off + 16 * c)
+                n = min(16, row_bytes - 16 * c)
+                assert np.array_equal(w[4:4 + n], want[16 * c:16 * c + n])
+                if c > 0:
+                    assert np.array_equal(w[:4], want[16 * c - 4:16 * c])
