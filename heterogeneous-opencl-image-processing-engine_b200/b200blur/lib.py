@@ -76,6 +76,7 @@ _SIGNATURES = {
     "b200blur_launch_rows_pitched": (c_int, [POINTER(Launch), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64,
                                              c_size_t, c_size_t, c_size_t, c_size_t]),
     "b200blur_enqueue_blur": (c_int, [c_void_p, c_int, POINTER(Launch), POINTER(c_int32)]),
+    "b200blur_enqueue_blur_batches": (c_int, [c_void_p, c_int, POINTER(Launch), c_int, POINTER(c_int32)]),
     "b200blur_launch_is_vectorised": (c_int, [POINTER(Launch)]),
     "b200blur_plan_row_edge": (c_int, [c_int, c_int, POINTER(ctypes.c_uint32)]),
     "b200blur_plan_groups": (c_int, [c_int, c_int, c_int, c_int64, c_size_t, c_int, c_int, POINTER(c_int64)]),
@@ -300,6 +301,13 @@ class Context:
     def enqueue_blur(self, queue, launch: Launch, want_event=False):
         ev = c_int32(-1)
         _check(self._lib.b200blur_enqueue_blur(self._h, queue, byref(launch), byref(ev) if want_event else None))
+        return ev.value if want_event else None
+
+    def enqueue_blur_batches(self, queue, launches, want_event=False):
+        """A list of independent launches of one geometry as ONE kernel launch with per-batch descriptors."""
+        arr = (Launch * len(launches))(*launches)
+        ev = c_int32(-1)
+        _check(self._lib.b200blur_enqueue_blur_batches(self._h, queue, arr, len(launches), byref(ev) if want_event else None))
         return ev.value if want_event else None
 
     def enqueue_marker(self, queue) -> int:

@@ -92,6 +92,8 @@ struct b200blur_ctx {
     uint8_t *scratch_in = nullptr, *scratch_out = nullptr;
     size_t scratch_bytes = 0;
     struct b200blur_feed *resident_feed = nullptr;   // descriptor table of b200blur_run_resident(coalesce = 0)
+    struct b200blur_feed *batches_feed = nullptr;    // descriptor table of b200blur_enqueue_blur_batches
+    int64_t batches_calls = 0;
     const void *resident_in = nullptr; void *resident_out = nullptr;   // ... and what it currently describes
     int64_t resident_n = 0, resident_calls = 0;
     cudaEvent_t fork_event = nullptr;          // fork/join of the per-batch launches of b200blur_run_resident
@@ -629,6 +631,8 @@ struct b200blur_feed {
     b200blur_ctx *ctx = nullptr;
     int width = 0, height = 0, channels = 0, max_batch = 0, cap = 0;
     size_t image_bytes = 0;
+    size_t in_stride = 0, out_stride = 0, top_stride = 0, bot_stride = 0;   // image strides shared by all batches
+    cudaEvent_t table_copied = nullptr;      // table mode: the last copy of the pinned mirror to the device has run
     StreamPlan plan;
     b200blur::FeedBatch *d_batches = nullptr, *h_batches = nullptr;   // device ring and its pinned host mirror
     unsigned long long *d_ctl = nullptr;     // [0] tail, [1] closed, [2] watchdog, [3] unused; [4],[5] work counters
@@ -654,6 +658,7 @@ void feed_release(b200blur_feed *f)
     if (f->h_batches) cudaFreeHost(f->h_batches);
     if (f->h_done) cudaFreeHost(f->h_done);
     if (f->h_ctl) cudaFreeHost(f->h_ctl);
+    if (f->table_copied) cudaEventDestroy(f->table_copied);
     if (f->kstream) cudaStreamDestroy(f->kstream);
     if (f->cstream) cudaStreamDestroy(f->cstream);
     delete f;
@@ -666,7 +671,8 @@ bool feed_eligible(int width, int height, int channels)
     return channels >= 1 && channels <= 4 && height >= 1 && row_bytes >= 256 && row_bytes % 16 == 0 && row_bytes <= 0x7fffffffULL;
 }
 
-int feed_build(b200blur_ctx *ctx, int width, int height, int channels, int max_batch, int cap, bool own_streams, b200blur_feed **out)
+int feed_build(b200blur_ctx *ctx, int width, int height, int channels, int max_batch, int cap, bool own_streams, b200blur_feed **out,
+               size_t in_stride = 0, size_t out_stride = 0, size_t top_stride = 0, size_t bot_stride = 0)
 {
     *out = nullptr;
     if (!feed_eligible(width, height, channels))
@@ -682,7 +688,14 @@ int feed_build(b200blur_ctx *ctx, int width, int height, int channels, int max_b
     if (const char *v = getenv("B200BLUR_FEED_TIMEOUT_MS")) f->timeout_ns = (unsigned long long)atoll(v) * 1000000ull;
     b200blur::BandParams p;
     memset(&p, 0, sizeof p);
-    p.in_stride = p.out_stride = f->image_bytes;
+    f->in_stride = in_stride ? in_stride : f->image_bytes;
+    f->out_stride = out_stride ? out_stride : f->image_bytes;
+    f->top_stride = top_stride;
+    f->bot_stride = bot_stride;
+    p.in_stride = f->in_stride;
+    p.out_stride = f->out_stride;
+    p.top_stride = top_stride;
+    p.bot_stride = bot_stride;
     p.row_bytes = p.pitch = p.out_pitch = width * channels;
     p.rows = height;
     p.width = width;
@@ -892,6 +905,7 @@ int b200blur_ctx_destroy(b200blur_ctx *ctx)
     for (auto q : ctx->queues) cudaStreamSynchronize(q);
     ring_release(ctx);
     if (ctx->resident_feed) feed_release(ctx->resident_feed);
+    if (ctx->batches_feed) feed_release(ctx->batches_feed);
     if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->scratch_in) cudaFree(ctx->scratch_in);
     if (ctx->scratch_out) cudaFree(ctx->scratch_out);
@@ -1221,6 +1235,84 @@ int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200blur_launch *l
     if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
     int nk;
     if (int rc = do_launch(ctx, queue, launch, &nk)) return event_abort(ctx, slot, ev, rc);
+    return event_end(ctx, queue, slot, ev);
+}
+
+int b200blur_enqueue_blur_batches(b200blur_ctx *ctx, int queue, const b200blur_launch *launches, int n_launches, b200blur_event *ev)
+{
+    if (int rc = queue_check(ctx, queue)) return rc;
+    if (n_launches < 0 || (n_launches > 0 && !launches)) return fail(B200BLUR_ERR_INVALID, "bad batch list");
+    for (int i = 0; i < n_launches; i++)
+        if (int rc = launch_validate(&launches[i])) return rc;
+    CU_TRY(cudaSetDevice(ctx->device));
+    int slot = -1;
+    // One kernel launch for all batches when they share one geometry the feed kernel can run: tight 16-byte-multiple rows,
+    // aligned pointers, same width / rows / channels / strides; each batch brings its own pointers (halo rows included)
+    // and image count.  Anything else is enqueued launch by launch -- same results.
+    bool same = n_launches >= 2 && ctx->kernel_variant != 1 && getenv("B200BLUR_NO_FEED") == nullptr;
+    int64_t max_n = 0;
+    if (same) {
+        const b200blur_launch &a = launches[0];
+        same = feed_eligible(a.width, a.rows, a.channels) && a.in_row_pitch == 0 && a.out_row_pitch == 0;
+        for (int i = 0; same && i < n_launches; i++) {
+            const b200blur_launch &l = launches[i];
+            same = l.width == a.width && l.rows == a.rows && l.channels == a.channels && l.in_row_pitch == 0 && l.out_row_pitch == 0 &&
+                   l.in_image_stride == a.in_image_stride && l.out_image_stride == a.out_image_stride && l.n_images >= 1 &&
+                   l.n_images <= 0x7fffffff && launch_vectorised(&l) &&
+                   (!l.halo_top || l.halo_top_stride == (a.halo_top ? a.halo_top_stride : l.halo_top_stride)) &&
+                   (!l.halo_bottom || l.halo_bottom_stride == (a.halo_bottom ? a.halo_bottom_stride : l.halo_bottom_stride)) &&
+                   (l.halo_top != nullptr) == (a.halo_top != nullptr) && (l.halo_bottom != nullptr) == (a.halo_bottom != nullptr);
+            if (l.n_images > max_n) max_n = l.n_images;
+        }
+    }
+    if (!same) {
+        if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
+        for (int i = 0; i < n_launches; i++) {
+            int nk;
+            if (int rc = do_launch(ctx, queue, &launches[i], &nk)) return event_abort(ctx, slot, ev, rc);
+        }
+        return event_end(ctx, queue, slot, ev);
+    }
+    const b200blur_launch &a = launches[0];
+    cudaStream_t s = ctx->queues[queue];
+    b200blur_feed *f = ctx->batches_feed;
+    const size_t top_stride = a.halo_top ? a.halo_top_stride : 0, bot_stride = a.halo_bottom ? a.halo_bottom_stride : 0;
+    if (!f || f->width != a.width || f->height != a.rows || f->channels != a.channels || f->max_batch != (int)max_n ||
+        f->cap != n_launches || f->in_stride != a.in_image_stride || f->out_stride != a.out_image_stride ||
+        f->top_stride != top_stride || f->bot_stride != bot_stride) {
+        if (f) {
+            for (auto q : ctx->queues) cudaStreamSynchronize(q);   // (the old table may be in use on any queue)
+            feed_release(f);
+            ctx->batches_feed = nullptr;
+        }
+        if (int rc = feed_build(ctx, a.width, a.rows, a.channels, (int)max_n, n_launches, false, &f, a.in_image_stride,
+                                a.out_image_stride, top_stride, bot_stride))
+            return rc;
+        ctx->batches_feed = f;
+    }
+    const long long total_groups = (long long)n_launches * f->plan.sp.feed_gpb;
+    if (total_groups >= 0x7fffffffLL) return fail(B200BLUR_ERR_INVALID, "too many work units in one batched enqueue");
+    // the pinned mirror may still be the source of the previous call's copy
+    if (!f->table_copied) CU_TRY(cudaEventCreateWithFlags(&f->table_copied, cudaEventDisableTiming));
+    else CU_TRY(cudaEventSynchronize(f->table_copied));
+    for (int i = 0; i < n_launches; i++) {
+        b200blur::FeedBatch &d = f->h_batches[i];
+        memset(&d, 0, sizeof d);
+        d.in = static_cast<const uint8_t *>(launches[i].in);
+        d.out = static_cast<uint8_t *>(launches[i].out);
+        d.top = static_cast<const uint8_t *>(launches[i].halo_top);
+        d.bot = static_cast<const uint8_t *>(launches[i].halo_bottom);
+        d.n_images = (int)launches[i].n_images;
+    }
+    f->h_ctl[0] = (unsigned long long)n_launches;
+    f->h_ctl[1] = 1ull;
+    // (the table is built before the event starts: `ev` times the copies of the descriptors and the kernel only)
+    if (int rc = event_begin(ctx, queue, ev, &slot)) return rc;
+    CU_TRY_EV(cudaMemcpyAsync(f->d_batches, f->h_batches, sizeof(b200blur::FeedBatch) * (size_t)n_launches, cudaMemcpyHostToDevice, s), slot, ev);
+    CU_TRY_EV(cudaMemcpyAsync(f->d_ctl, f->h_ctl, 16, cudaMemcpyHostToDevice, s), slot, ev);
+    CU_TRY_EV(cudaEventRecord(f->table_copied, s), slot, ev);
+    f->base = ctx->batches_calls++ * (int64_t)n_launches;
+    if (int rc = feed_launch(f, s, total_groups)) return event_abort(ctx, slot, ev, rc);
     return event_end(ctx, queue, slot, ev);
 }
 

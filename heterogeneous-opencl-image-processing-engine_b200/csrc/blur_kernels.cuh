@@ -270,14 +270,17 @@ struct StreamParams {
     unsigned long long feed_base;      // sequence number of the batch in descriptor-ring position 0 of this launch
 };
 
-// One batch of a feed: `n_images` tight images starting at `in`, results to `out` (image stride = rows * pitch).
+// One batch of a feed: `n_images` images starting at `in`, results to `out`, optional halo rows above / below the band
+// (Approach 2: rows of the neighbouring bands, possibly in another GPU's memory); strides are the feed's.
 struct FeedBatch {
     const uint8_t *in;
     uint8_t *out;
+    const uint8_t *top;
+    const uint8_t *bot;
     int n_images;
     int pad_[3];
 };
-static_assert(sizeof(FeedBatch) == 32, "FeedBatch is copied as two 16-byte words");
+static_assert(sizeof(FeedBatch) == 48, "FeedBatch is read as three 16-byte words");
 
 namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -785,10 +788,12 @@ blur_stream_kernel(const StreamParams sp)
                         const unsigned long long seq = sp.feed_base + b;
                         const int slot = (int)(seq % (unsigned long long)sp.feed_cap);
                         const uint4 *dp = reinterpret_cast<const uint4 *>(sp.batches + slot);
-                        const uint4 d0 = __ldcv(dp), d1 = __ldcv(dp + 1);
+                        const uint4 d0 = __ldcv(dp), d1 = __ldcv(dp + 1), d2 = __ldcv(dp + 2);
                         const uint8_t *bin = reinterpret_cast<const uint8_t *>(((unsigned long long)d0.y << 32) | d0.x);
                         uint8_t *bout = reinterpret_cast<uint8_t *>(((unsigned long long)d0.w << 32) | d0.z);
-                        const int n_images = (int)d1.x;
+                        const uint8_t *btop = reinterpret_cast<const uint8_t *>(((unsigned long long)d1.y << 32) | d1.x);
+                        const uint8_t *bbot = reinterpret_cast<const uint8_t *>(((unsigned long long)d1.w << 32) | d1.z);
+                        const int n_images = (int)d2.x;
                         const unsigned per_block = (unsigned)(sp.nseg * sp.ncb);
                         const unsigned ib = local / per_block;
                         const int img0 = (int)ib * sp.ipc;
@@ -801,7 +806,8 @@ blur_stream_kernel(const StreamParams sp)
                         decode_rows_cols(sp, local - ib * per_block, sp.seg, sp.b.rows, q);
                         q.n_img = min(sp.ipc, n_images - img0);
                         q.in = bin + (size_t)img0 * sp.b.in_stride;
-                        q.top = q.bot = nullptr;
+                        q.top = btop ? btop + (size_t)img0 * sp.b.top_stride : nullptr;
+                        q.bot = bbot ? bbot + (size_t)img0 * sp.b.bot_stride : nullptr;
                         m.out = bout + (size_t)img0 * sp.b.out_stride + (size_t)q.r0 * sp.b.out_pitch + q.x0;
                     }
                 }

@@ -182,6 +182,14 @@ B200BLUR_API int b200blur_launch_rows_pitched(b200blur_launch *l, const void *in
 /* clSetKernelArg x5 + clEnqueueNDRangeKernel (A1:366-389, :507): asynchronous, in order on `queue`. */
 B200BLUR_API int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200blur_launch *launch,
                                        b200blur_event *ev);
+/* The same for a LIST of launches that are independent of each other (batches): when they share one geometry (width,
+ * rows, channels, image and halo strides; tight rows of a 16-byte-multiple length, aligned pointers) they run as ONE
+ * kernel launch with per-batch descriptors -- each launch keeps its own in / out / halo pointers and image count, work
+ * units never span two of them, and the tail of one overlaps the start of the next instead of costing a launch ramp and
+ * drain each (Approach 2 bands of a small image on many GPUs: 47 us per pass as separate launches).
+ * Other lists are enqueued launch by launch.  Asynchronous, in order on `queue`; `ev` times the whole list. */
+B200BLUR_API int b200blur_enqueue_blur_batches(b200blur_ctx *ctx, int queue, const b200blur_launch *launches, int n_launches,
+                                               b200blur_event *ev);
 /* Which device code a launch would run: 1 = vectorised sm_100a stencil, 0 = generic path. */
 B200BLUR_API int b200blur_launch_is_vectorised(const b200blur_launch *launch);
 /* Select the kernel variant of the vectorised path (for profiling/tests): 0 = auto, 1 = register/shuffle
