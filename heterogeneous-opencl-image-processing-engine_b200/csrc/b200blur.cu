@@ -633,6 +633,7 @@ struct b200blur_feed {
     size_t image_bytes = 0;
     size_t in_stride = 0, out_stride = 0, top_stride = 0, bot_stride = 0;   // image strides shared by all batches
     cudaEvent_t table_copied = nullptr;      // table mode: the last copy of the pinned mirror to the device has run
+    cudaEvent_t table_kernel = nullptr;      // table mode: the last kernel reading the device table / counters has finished
     StreamPlan plan;
     b200blur::FeedBatch *d_batches = nullptr, *h_batches = nullptr;   // device ring and its pinned host mirror
     unsigned long long *d_ctl = nullptr;     // [0] tail, [1] closed, [2] watchdog, [3] unused; [4],[5] work counters
@@ -659,6 +660,7 @@ void feed_release(b200blur_feed *f)
     if (f->h_done) cudaFreeHost(f->h_done);
     if (f->h_ctl) cudaFreeHost(f->h_ctl);
     if (f->table_copied) cudaEventDestroy(f->table_copied);
+    if (f->table_kernel) cudaEventDestroy(f->table_kernel);
     if (f->kstream) cudaStreamDestroy(f->kstream);
     if (f->cstream) cudaStreamDestroy(f->cstream);
     delete f;
@@ -1292,9 +1294,15 @@ int b200blur_enqueue_blur_batches(b200blur_ctx *ctx, int queue, const b200blur_l
     }
     const long long total_groups = (long long)n_launches * f->plan.sp.feed_gpb;
     if (total_groups >= 0x7fffffffLL) return fail(B200BLUR_ERR_INVALID, "too many work units in one batched enqueue");
-    // the pinned mirror may still be the source of the previous call's copy
-    if (!f->table_copied) CU_TRY(cudaEventCreateWithFlags(&f->table_copied, cudaEventDisableTiming));
-    else CU_TRY(cudaEventSynchronize(f->table_copied));
+    // the pinned mirror may still be the source of the previous call's copy; the device table and its counters may still
+    // be in use by the previous call's kernel on ANOTHER queue (on the same queue stream order already covers it)
+    if (!f->table_copied) {
+        CU_TRY(cudaEventCreateWithFlags(&f->table_copied, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&f->table_kernel, cudaEventDisableTiming));
+    } else {
+        CU_TRY(cudaEventSynchronize(f->table_copied));
+        CU_TRY(cudaStreamWaitEvent(s, f->table_kernel, 0));
+    }
     for (int i = 0; i < n_launches; i++) {
         b200blur::FeedBatch &d = f->h_batches[i];
         memset(&d, 0, sizeof d);
@@ -1313,6 +1321,7 @@ int b200blur_enqueue_blur_batches(b200blur_ctx *ctx, int queue, const b200blur_l
     CU_TRY_EV(cudaEventRecord(f->table_copied, s), slot, ev);
     f->base = ctx->batches_calls++ * (int64_t)n_launches;
     if (int rc = feed_launch(f, s, total_groups)) return event_abort(ctx, slot, ev, rc);
+    CU_TRY_EV(cudaEventRecord(f->table_kernel, s), slot, ev);
     return event_end(ctx, queue, slot, ev);
 }
 

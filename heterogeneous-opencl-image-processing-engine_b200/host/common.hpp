@@ -122,6 +122,9 @@ struct ExtraOptions {
                                  //                          exercises the multi-GPU host logic on a single-GPU box)
     int fuse = 0;                // --fuse N               (batches per transfer/launch; 0 = automatic ~64 MB, 1 = the reference's granularity)
     bool static_split = false;   // --static-split         (Approach 1: fixed even partition per batch instead of work stealing)
+    bool stage_once = false;     // --stage-once           (every image of the stream is the same source image, so fill each
+                                 //                          pinned ring slot ONCE, before the timer, and re-send it per batch;
+                                 //                          the default re-fills per batch inside the timer like the reference)
 };
 
 inline int parse_extra(int argc, char **argv, int first, ExtraOptions &o)
@@ -147,6 +150,7 @@ inline int parse_extra(int argc, char **argv, int first, ExtraOptions &o)
         else if (a == "--ring") o.ring = atoi(val("--ring"));
         else if (a == "--oversubscribe") o.oversubscribe = true;
         else if (a == "--static-split") o.static_split = true;
+        else if (a == "--stage-once") o.stage_once = true;
         else if (a == "--fuse") o.fuse = atoi(val("--fuse"));
         else { printf("Error: unknown option %s\n", a.c_str()); return -1; }
     }

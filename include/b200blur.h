@@ -187,7 +187,8 @@ B200BLUR_API int b200blur_enqueue_blur(b200blur_ctx *ctx, int queue, const b200b
  * kernel launch with per-batch descriptors -- each launch keeps its own in / out / halo pointers and image count, work
  * units never span two of them, and the tail of one overlaps the start of the next instead of costing a launch ramp and
  * drain each (Approach 2 bands of a small image on many GPUs: 47 us per pass as separate launches).
- * Other lists are enqueued launch by launch.  Asynchronous, in order on `queue`; `ev` times the whole list. */
+ * Other lists are enqueued launch by launch.  Asynchronous, in order on `queue`; `ev` times the whole list.  The
+ * descriptor table belongs to the context: a call on another queue starts after the previous call's kernel. */
 B200BLUR_API int b200blur_enqueue_blur_batches(b200blur_ctx *ctx, int queue, const b200blur_launch *launches, int n_launches,
                                                b200blur_event *ev);
 /* Which device code a launch would run: 1 = vectorised sm_100a stencil, 0 = generic path. */

@@ -131,6 +131,24 @@ def test_split_image_blur_cli_eight_bands_stress(photo):
     assert sums[0] == sums[1]
 
 
+@pytest.mark.parametrize("prog,args", [("heterogeneous_blur", ["both", "0.5", "7"]), ("split_image_blur", ["0.5", "7"])])
+def test_cli_stage_once_gives_the_same_outputs(photo, prog, args):
+    """--stage-once fills every pinned ring slot once before the timer and re-sends it per batch (the stream is one image
+    repeated); every output byte (FNV-1a over all of them) must equal the default per-batch staging, ragged last batch and
+    ring wrap-around included."""
+    d, path, img, want = photo
+    sums = []
+    for i, extra in enumerate([[], ["--stage-once"]]):
+        out_path = os.path.join(d, f"{prog}_once_{i}.ppm")
+        text = run([os.path.join(BIN, prog)] + args + ["--images", "100", "--gpus", "2", "--oversubscribe", "--ring", "2",
+                    "--fuse", "1", "--input", path, "--save", out_path, "--quiet", "--checksum"] + extra, d)
+        assert "Total images processed: 100" in text
+        assert ("once per ring slot" in text) == bool(extra)
+        assert np.array_equal(read_ppm(out_path), want)
+        sums.append(_field(text, "Output checksum"))
+    assert sums[0] == sums[1]
+
+
 @pytest.mark.parametrize("name", ["420_q30_96x80.jpg", "420_photo_crop_80x50.jpg", "420_q75_odd_101x67.jpg"])
 def test_cli_blurs_a_jpeg_input(tmp_path, name):
     """Ingest -> hot path: the CLI decodes a .jpg itself (host/jpeg_decode.hpp, byte-identical to libjpeg) and its saved

@@ -226,3 +226,24 @@ def test_enqueue_blur_batches_with_halo_pointers(ctx, h, w, g, n):
     for d_in, d_out in bufs:
         ctx.dev_free(d_in)
         ctx.dev_free(d_out)
+
+
+def test_enqueue_blur_batches_from_alternating_queues(ctx):
+    """The descriptor table and its work counters belong to the context, not to a queue: calls that alternate between
+    queues (nothing but the library orders them) must not overwrite the table under the previous call's kernel.  Two
+    different lists of the same geometry, 12 calls round-robin over the queues, every output checked."""
+    h, w, c = 48, 320, 3
+    lists = []
+    for k in range(2):
+        xs = [synth(700 + 10 * k + i, m, h, w, c) for i, m in enumerate([40, 33, 40])]
+        bufs = [_upload(ctx, x) for x in xs]
+        lists.append((xs, bufs, [ctx.launch_rows(d_in, d_out, w, h, c, 0, h, x.shape[0]) for x, (d_in, d_out) in zip(xs, bufs)]))
+    ctx.finish()
+    for i in range(12):
+        ctx.enqueue_blur_batches(i % 4, lists[i % 2][2])        # the fixture context has 4 queues
+    ctx.finish()
+    for xs, bufs, _ in lists:
+        for x, (d_in, d_out) in zip(xs, bufs):
+            assert np.array_equal(_download(ctx, d_out, x), oracle.c_blur_batch(x, integer=True))
+            ctx.dev_free(d_in)
+            ctx.dev_free(d_out)
