@@ -36,3 +36,16 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def build_c_client(tmp_path):
+    """Compiles tests/c/abi_client.c (plain C99, -pedantic -Werror) against include/b200blur.h and links the built library."""
+    import subprocess
+    import b200blur
+    exe = os.path.join(str(tmp_path), "abi_client")
+    libdir = os.path.dirname(b200blur.lib_path())
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_client.c"), "-L", libdir, "-lb200blur", f"-Wl,-rpath,{libdir}", "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe

@@ -148,3 +148,17 @@ def test_band_plan_tiles_the_image_with_one_row_halos(h, g):
         assert p.input_rows == p.rows + p.has_top + p.has_bottom
     if h >= g:
         assert len(plans) == g and max(p.rows for p in plans) - min(p.rows for p in plans) <= 1
+
+
+def test_plain_c_host_compiles_links_and_runs(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit (the reference's hosts are C) includes the header with -pedantic
+    -Werror, links the library and makes the reference's host-side calls -- known answers from its logs and sources."""
+    import subprocess
+    from conftest import build_c_client
+    out = subprocess.run([build_c_client(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "FAIL" not in out.stdout and out.stdout.rstrip().endswith("done")
+    assert "split 10 25" in out.stdout          # heterogeneous_blur.c:449-451 at 0.728: 25 for the GPU, 10 for the CPU
+    assert "ok split row 39" in out.stdout      # split_image_blur.c:144 at 0.837
+    if b200blur.device_count() == 0:
+        assert "devices 0" in out.stdout and "checksum" not in out.stdout

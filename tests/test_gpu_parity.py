@@ -649,3 +649,20 @@ def test_large_frame(ctx):
     assert_same(y[:64], oracle.c_blur(x[:65], integer=True)[:64])
     assert_same(y[1000:1060], oracle.c_blur(x[999:1061], integer=True)[1:61])
     assert_same(y[-64:], oracle.c_blur(x[-65:], integer=True)[1:])
+
+
+def test_plain_c_host_blurs_an_image_through_the_abi(tmp_path):
+    """tests/c/abi_client.c: a C99 program (no Python, no ctypes) does write -> blur -> read on one 320x240 image and prints
+    an FNV-1a checksum of the output; the oracle's blur of the same bytes must give the same checksum."""
+    import subprocess
+    from conftest import build_c_client
+    out = subprocess.run([build_c_client(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "FAIL" not in out.stdout, out.stdout + out.stderr
+    got = [line.split()[1] for line in out.stdout.splitlines() if line.startswith("checksum ")]
+    w, h, c = 320, 240, 3
+    i = np.arange(w * h * c, dtype=np.uint64)
+    x = ((i * np.uint64(2654435761)) >> np.uint64(13)).astype(np.uint8).reshape(h, w, c)
+    s = 1469598103934665603
+    for b in oracle.c_blur(x).tobytes():
+        s = ((s ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert got == ["%016x" % s]
