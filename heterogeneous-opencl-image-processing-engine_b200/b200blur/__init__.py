@@ -22,6 +22,7 @@ from .lib import (  # noqa: F401
     plan_row_edge,
     ratio_split_images,
     ratio_split_row,
+    run_host_multi,
     version,
     DECLARED_SYMBOLS,
 )

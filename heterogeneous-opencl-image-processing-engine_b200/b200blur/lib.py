@@ -88,6 +88,8 @@ _SIGNATURES = {
     "b200blur_run_resident": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int,
                                       POINTER(Stats)]),
     "b200blur_run_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, POINTER(Stats)]),
+    "b200blur_run_host_multi": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int,
+                                        POINTER(Stats)]),
     "b200blur_feed_create": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
     "b200blur_feed_destroy": (c_int, [c_void_p]),
     "b200blur_feed_start": (c_int, [c_void_p]),
@@ -180,6 +182,17 @@ def ratio_split_row(height: int, gpu_ratio: float) -> int:
     s = c_int()
     _check(load().b200blur_ratio_split_row(height, gpu_ratio, byref(s)))
     return s.value
+
+
+def run_host_multi(ctxs, h_in, h_out, width, height, channels, n_images, batch_size):
+    """One host stream over several contexts (GPUs) in one call (b200blur_run_host_multi): the contexts' pipelines take
+    transfer chunks from a shared counter.  -> list of Stats, one per context."""
+    n = len(ctxs)
+    handles = (c_void_p * n)(*[c._h for c in ctxs])
+    stats = (Stats * n)()
+    _check(load().b200blur_run_host_multi(handles, n, _ptr(h_in), _ptr(h_out), width, height, channels, n_images,
+                                          batch_size, stats))
+    return list(stats)
 
 
 def plan_row_edge(row_bytes: int, channels: int):

@@ -11,12 +11,14 @@
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "blur_kernels.cuh"
@@ -1762,8 +1764,12 @@ static int ring_prepare(b200blur_ctx *ctx, size_t slot_bytes, size_t tight_bytes
     return B200BLUR_OK;
 }
 
-int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int width, int height, int channels,
-                      int64_t n_images, int batch_size, b200blur_stats *stats)
+// The end-to-end pipeline of one context.  `shared_next` == nullptr: this context moves every chunk of the stream, in
+// order.  Otherwise the chunk indices are TAKEN from *shared_next (b200blur_run_host_multi: several contexts, one host
+// thread each, draining one stream); `n_workers` only sizes the chunks so that every worker keeps a full pipeline.
+static int run_host_impl(b200blur_ctx *ctx, const void *h_in, void *h_out, int width, int height, int channels,
+                         int64_t n_images, int batch_size, b200blur_stats *stats, std::atomic<int64_t> *shared_next,
+                         int n_workers)
 {
     if (int rc = ctx_check(ctx)) return rc;
     if (batch_size < 1) return fail(B200BLUR_ERR_INVALID, "batch_size %d < 1", batch_size);
@@ -1787,7 +1793,7 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
         if (batch_bytes < target) {
             long long fuse = (long long)(target / batch_bytes + 0.5);
             const long long n_batches = (n_images + batch_size - 1) / batch_size;
-            if (fuse > n_batches / 16) fuse = n_batches / 16;   // keep at least ~16 chunks in the pipeline
+            if (fuse > n_batches / (16 * n_workers)) fuse = n_batches / (16 * n_workers);   // keep at least ~16 chunks in every pipeline
             if (fuse < 1) fuse = 1;
             chunk = (long long)batch_size * fuse;
         } else if (batch_bytes > 2 * target) {
@@ -1826,8 +1832,8 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
     };
 
     // One chunk's three stages.  `phase`: 0 = all three, 1 = upload + kernel only, 2 = download only.
-    auto issue = [&](int64_t ci, int phase) -> int {
-        b200blur_ctx::Slot &s = ctx->ring[ci % n_slots];
+    auto issue = [&](int64_t ci, int phase, int64_t slot_index) -> int {
+        b200blur_ctx::Slot &s = ctx->ring[slot_index % n_slots];
         const int64_t i0 = ci * batch_size;
         const int64_t n = (n_images - i0 < batch_size) ? n_images - i0 : batch_size;
         const size_t bytes = (size_t)n * image_bytes;
@@ -1879,12 +1885,26 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
     // profiles/r02_linkbench_n8.txt): 64 GB/s each way with all 16 flows at once, 75 GB/s each way with half the GPUs
     // uploading while the other half download.  Processes are not synchronised with each other; their waves interleave.
     const char *env_phased = getenv("B200BLUR_E2E_PHASED");
-    const bool phased = env_phased && atoi(env_phased) != 0;
-    if (!phased) {
+    const bool phased = env_phased && atoi(env_phased) != 0 && !shared_next;
+    int64_t taken = n_chunks, images_done = n_images;   // chunks / images this context moved
+    if (shared_next) {
+        // take the next chunk only when a ring slot is free for it: a GPU behind a slower link takes fewer
+        taken = images_done = 0;
+        for (;;) {
+            if (taken >= n_slots)
+                if (int rc = harvest(ctx->ring[taken % n_slots])) return rc;
+            const int64_t ci = shared_next->fetch_add(1, std::memory_order_relaxed);
+            if (ci >= n_chunks) break;
+            if (int rc = issue(ci, 0, taken)) return rc;
+            const int64_t i0 = ci * batch_size;
+            images_done += (n_images - i0 < batch_size) ? n_images - i0 : batch_size;
+            taken++;
+        }
+    } else if (!phased) {
         for (int64_t ci = 0; ci < n_chunks; ci++) {
             if (ci >= n_slots)
                 if (int rc = harvest(ctx->ring[ci % n_slots])) return rc;  // slot's previous chunk fully drained (also frees d_in/d_out)
-            if (int rc = issue(ci, 0)) return rc;
+            if (int rc = issue(ci, 0, ci)) return rc;
         }
     } else {
         for (int64_t w0 = 0; w0 < n_chunks; w0 += n_slots) {
@@ -1894,16 +1914,18 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
                     if (int rc = harvest(ctx->ring[ci % n_slots])) return rc;   // the previous wave's downloads are done
             }
             for (int64_t ci = w0; ci < w1; ci++)
-                if (int rc = issue(ci, 1)) return rc;
+                if (int rc = issue(ci, 1, ci)) return rc;
             // downloads start when the wave's last upload has finished
             CU_TRY(cudaStreamWaitEvent(q_out, ctx->ring[(w1 - 1) % n_slots].ev[1], 0));
             for (int64_t ci = w0; ci < w1; ci++)
-                if (int rc = issue(ci, 2)) return rc;
+                if (int rc = issue(ci, 2, ci)) return rc;
         }
     }
-    int64_t first_pending = n_chunks > n_slots ? n_chunks - n_slots : 0;
+    // (with a shared counter the slot that was harvested before the failed take must not be harvested twice)
+    int64_t first_pending = taken > n_slots ? taken - n_slots : 0;
+    if (shared_next && taken >= n_slots) first_pending++;
     if (phased && n_chunks > 0) first_pending = (n_chunks - 1) / n_slots * n_slots;   // earlier waves were harvested
-    for (int64_t ci = first_pending; ci < n_chunks; ci++)
+    for (int64_t ci = first_pending; ci < taken; ci++)
         if (int rc = harvest(ctx->ring[ci % n_slots])) return rc;
     CU_TRY(cudaStreamSynchronize(q_out));
     if (stats) {
@@ -1912,11 +1934,51 @@ int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int widt
         stats->h2d_ms = ms_in;
         stats->kernel_ms = ms_k;
         stats->d2h_ms = ms_out;
-        stats->images = n_images;
+        stats->images = images_done;
         stats->launches = launches;
-        stats->h2d_bytes = (int64_t)(image_bytes * (size_t)n_images);
-        stats->d2h_bytes = (int64_t)(image_bytes * (size_t)n_images);
+        stats->h2d_bytes = (int64_t)(image_bytes * (size_t)images_done);
+        stats->d2h_bytes = (int64_t)(image_bytes * (size_t)images_done);
     }
+    return B200BLUR_OK;
+}
+
+int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int width, int height, int channels,
+                      int64_t n_images, int batch_size, b200blur_stats *stats)
+{
+    return run_host_impl(ctx, h_in, h_out, width, height, channels, n_images, batch_size, stats, nullptr, 1);
+}
+
+int b200blur_run_host_multi(b200blur_ctx *const *ctxs, int n_ctx, const void *h_in, void *h_out, int width, int height,
+                            int channels, int64_t n_images, int batch_size, b200blur_stats *stats)
+{
+    if (!ctxs || n_ctx < 1 || n_ctx > 64) return fail(B200BLUR_ERR_INVALID, "need 1..64 contexts");
+    for (int k = 0; k < n_ctx; k++) {
+        if (int rc = ctx_check(ctxs[k])) return rc;
+        for (int j = 0; j < k; j++)
+            if (ctxs[j] == ctxs[k]) return fail(B200BLUR_ERR_INVALID, "context %d is listed twice", k);
+    }
+    if (n_ctx == 1) return run_host_impl(ctxs[0], h_in, h_out, width, height, channels, n_images, batch_size, stats, nullptr, 1);
+    // one host thread per context (the reference's two devices share one thread and one clFinish, A1:538-539); the
+    // threads' pipelines take transfer chunks from one counter until the stream is drained
+    std::atomic<int64_t> next{0};
+    std::vector<int> rcs((size_t)n_ctx, B200BLUR_OK);
+    std::vector<std::string> errors((size_t)n_ctx);
+    std::vector<b200blur_stats> local((size_t)n_ctx);
+    auto work = [&](int k) {
+        rcs[k] = run_host_impl(ctxs[k], h_in, h_out, width, height, channels, n_images, batch_size, &local[k], &next, n_ctx);
+        if (rcs[k] != B200BLUR_OK) {
+            errors[k] = g_last_error;                       // (thread-local: carry it to the caller's thread)
+            next.store(INT64_MAX / 2, std::memory_order_relaxed);   // the others stop taking chunks
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int k = 1; k < n_ctx; k++) threads.emplace_back(work, k);
+    work(0);
+    for (auto &t : threads) t.join();
+    for (int k = 0; k < n_ctx; k++)
+        if (rcs[k] != B200BLUR_OK) return fail(rcs[k], "context %d: %s", k, errors[k].c_str());
+    if (stats)
+        for (int k = 0; k < n_ctx; k++) stats[k] = local[k];
     return B200BLUR_OK;
 }
 

@@ -256,6 +256,16 @@ B200BLUR_API int b200blur_run_resident(b200blur_ctx *ctx, const void *d_in, void
  * reports the kernels actually launched.  Odd widths are re-pitched by the strided copies on the way in and out. */
 B200BLUR_API int b200blur_run_host(b200blur_ctx *ctx, const void *h_in, void *h_out, int width, int height,
                                    int channels, int64_t n_images, int batch_size, b200blur_stats *stats);
+/* The same stream over SEVERAL GPUs in one call -- Approach 1's "split every batch between the devices" (A1:446-458)
+ * without a ratio: one host thread per context runs the pipeline above, and the pipelines TAKE transfer chunks from one
+ * shared counter whenever a ring slot is free, so a GPU behind a slower path to host memory simply moves fewer chunks
+ * (dynamic scheduling instead of the hand-tuned gpu_ratio, A1:713-722).  `ctxs` are n_ctx distinct
+ * contexts (usually one per GPU), each with >= 3 queues and used by no other thread during the call; h_in / h_out
+ * must be visible to every device (b200blur_host_alloc memory is).  stats, if given, has n_ctx entries: stats[k].images
+ * is what context k moved, wall_ms its own wall clock.  n_ctx == 1 is b200blur_run_host. */
+B200BLUR_API int b200blur_run_host_multi(b200blur_ctx *const *ctxs, int n_ctx, const void *h_in, void *h_out, int width,
+                                         int height, int channels, int64_t n_images, int batch_size,
+                                         b200blur_stats *stats);
 
 /* ---------------------------------------------------------------------------------------------------- feed
  * The batch loop of A1:418-600 as a RESIDENT kernel: instead of one kernel launch per batch (per image in the

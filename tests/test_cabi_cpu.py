@@ -52,6 +52,15 @@ def test_version_and_error_string():
     assert b"bad partition" in lib.b200blur_last_error()
 
 
+def test_run_host_multi_validates_its_context_list():
+    lib = b200blur.load()
+    assert lib.b200blur_run_host_multi(None, 2, None, None, 16, 16, 3, 0, 1, None) == L.ERR_INVALID
+    arr = (ctypes.c_void_p * 1)(None)
+    assert lib.b200blur_run_host_multi(arr, 0, None, None, 16, 16, 3, 0, 1, None) == L.ERR_INVALID
+    assert lib.b200blur_run_host_multi(arr, 1, None, None, 16, 16, 3, 0, 1, None) == L.ERR_INVALID   # NULL context
+    assert b"context" in lib.b200blur_last_error()
+
+
 def test_no_device_fails_loudly_not_silently():
     if b200blur.device_count() > 0:
         pytest.skip("a CUDA device is present")

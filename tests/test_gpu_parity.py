@@ -666,3 +666,41 @@ def test_plain_c_host_blurs_an_image_through_the_abi(tmp_path):
     for b in oracle.c_blur(x).tobytes():
         s = ((s ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     assert got == ["%016x" % s]
+
+
+@pytest.mark.parametrize("n_ctx,n,batch_size,chunk_mb,shape", [
+    (2, 300, 35, 4, (240, 320, 3)),      # many chunks: both pipelines wrap their rings several times
+    (3, 41, 1, 1, (64, 320, 3)),         # fewer chunks than a ring holds for some workers
+    (4, 7, 3, 0, (32, 256, 3)),          # more workers than chunks: some take nothing
+    (2, 120, 16, 2, (50, 250, 3)),       # odd width (tight rows, one-pass form) through the shared-counter pipeline
+])
+def test_run_host_multi_contexts_take_chunks_from_one_counter(monkeypatch, n_ctx, n, batch_size, chunk_mb, shape):
+    """b200blur_run_host_multi: one host stream, several contexts (one per GPU when the box has them, else all on GPU 0),
+    one host thread each inside the library, transfer chunks TAKEN from a shared counter (the library form of Approach 1's
+    work distribution, heterogeneous_blur.c:446-458, without a ratio).  Every image is processed exactly once: the output
+    equals the oracle's, and the per-context image counts add up to the stream."""
+    import torch
+    h, w, c = shape
+    monkeypatch.setenv("B200BLUR_E2E_CHUNK_MB", str(chunk_mb))
+    g = max(1, torch.cuda.device_count())
+    ctxs = [b200blur.Context(k % g, 3) for k in range(n_ctx)]
+    try:
+        x = synth(n * 7 + n_ctx, n, h, w, c)
+        h_in = torch.from_numpy(x).pin_memory()
+        h_out = torch.full_like(h_in, 0xA5).pin_memory()
+        for _ in range(2):                                   # twice: rings and kernels are warm the second time
+            stats = b200blur.run_host_multi(ctxs, h_in, h_out, w, h, c, n, batch_size)
+            assert len(stats) == n_ctx and sum(s.images for s in stats) == n
+            assert sum(s.h2d_bytes for s in stats) == x.nbytes and sum(s.d2h_bytes for s in stats) == x.nbytes
+            assert_same(h_out.numpy(), oracle.c_blur_batch(x, integer=True))
+            h_out.fill_(0xA5)
+        # one context = b200blur_run_host
+        st = b200blur.run_host_multi(ctxs[:1], h_in, h_out, w, h, c, n, batch_size)
+        assert st[0].images == n
+        assert_same(h_out.numpy(), oracle.c_blur_batch(x, integer=True))
+        # the same context twice is refused
+        with pytest.raises(b200blur.BlurError):
+            b200blur.run_host_multi([ctxs[0], ctxs[0]], h_in, h_out, w, h, c, n, batch_size)
+    finally:
+        for cx in ctxs:
+            cx.close()
