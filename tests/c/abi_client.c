@@ -74,6 +74,29 @@ int main(void)
         for (i = 0; i < bytes; i++) sum = (sum ^ ((unsigned char *)h_out)[i]) * 1099511628211ull;
         printf("input_rule (i*2654435761)>>13\nchecksum %016llx\n", sum);
         b200blur_event_release(ctx, ev);
+        {
+            /* the whole batch loop in one call (heterogeneous_blur.c:418-600): 8 replicas of the image, batch_size 3,
+             * through the multi-GPU entry point with a one-context list; every replica must equal the output above */
+            enum { N = 8 };
+            void *s_in = NULL, *s_out = NULL;
+            b200blur_ctx *list[1];
+            b200blur_ctx *ctx3 = NULL;
+            b200blur_stats st;
+            int k, same = 1;
+            CHECK(b200blur_ctx_create(0, 3, &ctx3) == B200BLUR_OK, "context with three queues");
+            list[0] = ctx3;
+            CHECK(b200blur_host_alloc(N * bytes, &s_in) == B200BLUR_OK && b200blur_host_alloc(N * bytes, &s_out) == B200BLUR_OK,
+                  "pinned stream buffers");
+            for (k = 0; k < N; k++) memcpy((unsigned char *)s_in + k * bytes, h_in, bytes);
+            memset(s_out, 0, N * bytes);
+            CHECK(b200blur_run_host_multi(list, 1, s_in, s_out, W, H, C, N, 3, &st) == B200BLUR_OK && st.images == N,
+                  "stream engine");
+            for (k = 0; k < N; k++) same = same && memcmp((unsigned char *)s_out + k * bytes, h_out, bytes) == 0;
+            CHECK(same, "every replica equals the single-image result");
+            b200blur_host_free(s_in);
+            b200blur_host_free(s_out);
+            CHECK(b200blur_ctx_destroy(ctx3) == B200BLUR_OK, "second context destroyed");
+        }
         b200blur_dev_free(ctx, d_in);
         b200blur_dev_free(ctx, d_out);
         b200blur_host_free(h_in);
