@@ -94,3 +94,44 @@ def test_plan_rejects_what_the_streamed_kernel_cannot_run():
     for bad in [(16, 16, 3, 10, 0), (320, 240, 5, 10, 0), (320, 240, 3, 10, 1000), (320, 240, 3, 0, 0), (250, 10, 3, 4, 0)]:
         with pytest.raises(b200blur.BlurError):
             b200blur.plan_groups(*bad)
+
+
+def _drain_with_shared_counter(n_chunks, n_slots, n_workers, rng):
+    """The control flow of run_host_impl with a shared chunk counter (csrc/b200blur.cu), restated: every worker harvests
+    the ring slot it is about to reuse BEFORE taking the next chunk index, stops at the first index past the stream, and
+    finally harvests what is still pending.  Returns per-worker (issued, harvested) lists of local chunk numbers."""
+    nxt = 0
+    state = [dict(taken=0, issued=[], harvested=[], done=False) for _ in range(n_workers)]
+    while not all(s["done"] for s in state):
+        s = state[int(rng.integers(0, n_workers))]          # any interleaving of the workers' loop iterations
+        if s["done"]:
+            continue
+        if s["taken"] >= n_slots:
+            s["harvested"].append(s["taken"] - n_slots)      # harvest(ring[taken % n_slots]) = local chunk taken - n_slots
+        ci, nxt = nxt, nxt + 1
+        if ci >= n_chunks:
+            first_pending = s["taken"] - n_slots if s["taken"] > n_slots else 0
+            if s["taken"] >= n_slots:
+                first_pending += 1
+            s["harvested"].extend(range(first_pending, s["taken"]))
+            s["done"] = True
+            continue
+        s["issued"].append(ci)
+        s["taken"] += 1
+    return state
+
+
+@pytest.mark.parametrize("n_chunks,n_slots,n_workers", [(0, 4, 2), (1, 4, 3), (4, 4, 1), (5, 4, 1), (17, 4, 2), (64, 2, 3),
+                                                        (9, 4, 8), (100, 4, 8), (33, 3, 5)])
+def test_shared_counter_pipeline_moves_and_harvests_every_chunk_once(n_chunks, n_slots, n_workers):
+    """b200blur_run_host_multi's host logic: over random interleavings of the workers, every chunk of the stream is issued
+    by exactly one worker, and every worker harvests each of its own chunks exactly once (a slot harvested twice would
+    add its stage times twice; one never harvested could still be in flight when the call returns)."""
+    import numpy as np
+    for seed in range(20):
+        state = _drain_with_shared_counter(n_chunks, n_slots, n_workers, np.random.default_rng(seed))
+        issued = sorted(c for s in state for c in s["issued"])
+        assert issued == list(range(n_chunks))
+        for s in state:
+            assert sorted(s["harvested"]) == list(range(s["taken"])), (seed, s)
+            assert len(s["harvested"]) == len(set(s["harvested"]))
